@@ -1,0 +1,79 @@
+"""ctypes face of tests/emu/libbgemu.so — the product's warp-level device code run on the CPU
+warp emulator.  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.oracle import State, Projector, u64_array
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_P = C.POINTER
+
+
+def compact_state(s, A):
+    """Active-mask layout -> contiguous layout (active rows first, order preserved)."""
+    n = s.n
+    act = [v for v in range(n) if (A >> v) & 1]
+    perm = act + [v for v in range(n) if not (A >> v) & 1]
+    k = len(act)
+    o = State()
+    o.n, o.k, o.Q, o.h = n, k, s.Q, s.h
+    d1 = d2 = 0
+    for r, v in enumerate(perm):
+        o.G[r] = s.G[v]
+        o.Gbar[r] = s.Gbar[v]
+        if r < k:
+            d1 |= ((s.D1 >> v) & 1) << r
+            d2 |= ((s.D2 >> v) & 1) << r
+            row = 0
+            for c in range(k):
+                row |= ((s.J[v] >> perm[c]) & 1) << c
+            o.J[r] = row
+    o.D1, o.D2 = d1, d2
+    return o
+
+
+class Emu:
+    def __init__(self):
+        subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+        lib = C.CDLL(os.path.join(HERE, "libbgemu.so"))
+        lib.emu_inner_product.argtypes = [_P(State), _P(State), _P(C.c_int32)]
+        lib.emu_terms.argtypes = [_P(State), _P(Projector), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_uint64),
+                                  _P(C.c_int32), _P(C.c_int), _P(C.c_int), _P(C.c_longlong)]
+        lib.emu_terms.restype = C.c_int
+        lib.emu_measure_pauli.argtypes = [_P(State), _P(C.c_uint64), C.c_int, C.c_uint64, C.c_uint64]
+        lib.emu_measure_pauli.restype = C.c_int
+        lib.emu_random_state.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(State),
+                                         _P(C.c_uint64)]
+        self.lib = lib
+
+    def inner_product(self, a, b):
+        out = (C.c_int32 * 3)()
+        self.lib.emu_inner_product(C.byref(a), C.byref(b), out)
+        return tuple(out)
+
+    def terms(self, theta, P, project, exact, t, terms):
+        n = len(terms)
+        epm = np.zeros((n, 3), dtype=np.int32)
+        npf, k = C.c_int(), C.c_int()
+        zw = (C.c_longlong * 4)()
+        alive = self.lib.emu_terms(C.byref(theta), C.byref(P), int(project), int(bool(exact)), t, n,
+                                   u64_array(terms), epm.ctypes.data_as(_P(C.c_int32)), C.byref(npf),
+                                   C.byref(k), zw)
+        return dict(alive=alive, epm=epm, npf=npf.value, k=k.value, zw=list(zw))
+
+    def measure_pauli(self, s, m, zeta, xi):
+        """returns (code, state in contiguous layout); code 0 annihilated, 1 unchanged, 2 factor 2^-1/2"""
+        w = s.copy()
+        A = C.c_uint64()
+        code = self.lib.emu_measure_pauli(C.byref(w), C.byref(A), m, zeta, xi)
+        return code, compact_state(w, A.value)
+
+    def random_state(self, n, seed, bin_, sample, cdf):
+        out = State()
+        A = C.c_uint64()
+        arr = (C.c_double * len(cdf))(*cdf)
+        self.lib.emu_random_state(n, seed, bin_, sample, arr, C.byref(out), C.byref(A))
+        return compact_state(out, A.value)
