@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — stabilizer inner products/sec on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME]
+    (N > 1: launched by the driver under torchrun, one rank per GPU)
+
+Workload (config.workload): BASELINE configs[3] — random hidden-shift circuit, n=40 qubits,
+t=40 T gates, |L> decomposition with k=9 (chi=512), L=2^16 random stabilizer states per projector.
+Input = the instruction stream the reference's unmodified front end wrote for that circuit
+(tests/golden/streams/hs_t40_k9_bit0.txt; generator: tests/golden/make_fixtures.py).
+One STEP = one probability() back-end evaluation = both projectors (G', H'):
+2 x 2^16 x 512 = 67,108,864 stabilizer inner products (+ the 2 x 2^16 theta draws and projections).
+Samples are sharded by stride across ranks (weak scaling is NOT used: total work is fixed... see
+`scaling`), partial sums are all-reduced over NCCL inside the library.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STREAMS = os.path.join(ROOT, "tests", "golden", "streams")
+CONFIGS = {
+    # name: (stream file, samples per projector, forced k for |L>, description)
+    "hidden_shift_n40_t40_k9_L65536": ("hs_t40_k9_bit0.txt", 65536, 9,
+                                       "random hidden-shift n=40, t=40 T gates, |L> k=9 (chi=512), L=2^16"),
+    "hidden_shift_n40_t16_L16384": ("hs_t16_bit6.txt", 16384, 0,
+                                    "random hidden-shift n=40, t=16 T gates, exact |H^t> (chi=256), L=2^14"),
+    "htstack_t4_L1024": ("htstack_t4.txt", 1024, 0, "HTstack.circ output 0, t=4 (chi=4), L=1024"),
+}
+DEFAULT_CONFIG = "hidden_shift_n40_t40_k9_L65536"
+
+
+def parse_stream(path):
+    """13 scalars + 2 projectors (libcirc/probability.c:74-127, libcirc/utils/comms.c:9-36)."""
+    tok = open(path).read().split()
+    it = iter(tok)
+    names = ["quiet", "verbose", "noapprox", "samples", "bins", "t", "k", "exact", "fidbound",
+             "fidelity", "rank", "forceL", "forceSample"]
+    cfg = {}
+    for nme in names:
+        v = next(it)
+        cfg[nme] = float(v) if nme == "fidbound" else int(float(v))
+    projs = []
+    for _ in range(2):
+        ns, nq = int(next(it)), int(next(it))
+        ph, xs, zs = [], [], []
+        for _i in range(ns):
+            ph.append(int(next(it)) % 4)
+            x = z = 0
+            for q in range(nq):
+                if int(next(it)):
+                    x |= 1 << q
+                if int(next(it)):
+                    z |= 1 << q
+            xs.append(x)
+            zs.append(z)
+        projs.append((nq, ph, xs, zs))
+    return cfg, projs[0], projs[1]
+
+
+def fixed_L(k, t):
+    """The k x t matrix L: uniform random bits (BitMatrixSetRandom, libcirc/utils/matrix.c:301-306),
+    fixed by seed so that every arm / rank / run sees the same decomposition."""
+    import numpy as np
+    rs = np.random.RandomState(20240)
+    return [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in ln.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for j, nme in enumerate(names):
+                if len(r) > 5 + j and r[5 + j].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, cfgname):
+    """--impl reference: the reference's own C implementation (oracle/_ref/mpibackend_ref, the
+    unmodified sources behind a single-rank MPI shim, -O2) on the host cores: one process per core,
+    each on a disjoint shard of samples — what the reference's MPI rank stride does
+    (libcirc/probability.c:268).  Each step is a BOUNDED sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    stream, samples, k, desc = CONFIGS[cfgname]
+    cfg, G, H = parse_stream(os.path.join(STREAMS, stream))
+    t = cfg["t"]
+    exact = cfg["exact"] if k == 0 else 0
+    chi = (1 << ((t + 1) // 2)) if exact else (1 << k)
+    exe = os.path.join(ROOT, "oracle", "_ref", "mpibackend_ref")
+    kind = "reference"
+    cores = os.cpu_count() or 1
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/mpibackend_ref not built"}))
+        return
+    # bounded sample: each core evaluates `per_core` samples of each projector
+    rate_guess = 14.0 if t >= 33 else 700.0            # pairs/s/core measured in the build container
+    per_core = max(1, int(round(rate_guess * 4.0 / (2 * chi))))     # ~4 s per step
+    tok = open(os.path.join(STREAMS, stream)).read().split()
+    tok[3] = str(per_core)        # samples
+    tok[6] = str(k)               # k
+    tok[7] = str(int(bool(exact)))
+    tok[12] = "1"                 # forceSample: stay on the sampled path
+    text = "\n".join(tok) + "\n"
+
+    def step():
+        procs = [subprocess.Popen([exe, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL) for _ in range(cores)]
+        for p in procs:
+            p.stdin.write(text.encode())
+            p.stdin.close()
+        for p in procs:
+            p.stdout.read()
+            p.wait()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    pairs_per_step = cores * per_core * 2 * chi
+    value = pairs_per_step * args.steps / dt
+    line = {"metric": "stabilizer inner products/sec", "value": value, "unit": "inner products/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 bit rows + Z8 integer phases", "data": "synthetic",
+            "config": {"workload": cfgname, "description": desc, "t": t, "chi": chi,
+                       "samples_per_projector": samples},
+            "cpu_baseline": {"value": value, "unit": "inner products/s", "cores": cores, "kind": kind,
+                             "sample": "%d processes x %d samples x 2 projectors x %d terms per step "
+                                       "(reference C sources unmodified, gcc -O2, single-rank MPI shim)"
+                                       % (cores, per_core, chi)},
+            "e2e": {"value": value, "unit": "inner products/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(cfgname, seconds=12.0):
+    """Reported baseline next to the GPU number (rank 0, N=1): the compiled reference on all host
+    cores for a bounded sample."""
+    class A:
+        pass
+    stream, samples, k, desc = CONFIGS[cfgname]
+    cfg, G, H = parse_stream(os.path.join(STREAMS, stream))
+    t = cfg["t"]
+    exact = cfg["exact"] if k == 0 else 0
+    chi = (1 << ((t + 1) // 2)) if exact else (1 << k)
+    exe = os.path.join(ROOT, "oracle", "_ref", "mpibackend_ref")
+    cores = os.cpu_count() or 1
+    if not os.path.exists(exe):
+        return None
+    rate_guess = 14.0 if t >= 33 else 700.0
+    per_core = max(1, int(round(rate_guess * seconds / (2 * chi))))
+    tok = open(os.path.join(STREAMS, stream)).read().split()
+    tok[3], tok[6], tok[7], tok[12] = str(per_core), str(k), str(int(bool(exact))), "1"
+    text = ("\n".join(tok) + "\n").encode()
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([exe, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                              stderr=subprocess.DEVNULL) for _ in range(cores)]
+    for p in procs:
+        p.stdin.write(text)
+        p.stdin.close()
+    for p in procs:
+        p.stdout.read()
+        p.wait()
+    dt = time.perf_counter() - t0
+    pairs = cores * per_core * 2 * chi
+    return {"value": pairs / dt, "unit": "inner products/s", "cores": cores, "kind": "reference",
+            "sample": "%d processes x %d samples x 2 projectors x %d terms in %.1f s (reference C sources "
+                      "unmodified, gcc -O2, single-rank MPI shim)" % (cores, per_core, chi, dt)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfgname = args.config
+    if args.impl == "reference":
+        return run_reference(args, cfgname)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import circuitsimulator_b200 as bg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    stream, samples, k, desc = CONFIGS[cfgname]
+    cfg, Gd, Hd = parse_stream(os.path.join(STREAMS, stream))
+    t = cfg["t"]
+    exact = cfg["exact"] if k == 0 else 0
+    L = [] if exact else fixed_L(k, t)
+    chi = (1 << ((t + 1) // 2)) if exact else (1 << k)
+    G = bg.Projector.make(*Gd)
+    H = bg.Projector.make(*Hd)
+
+    # two contexts on this GPU (one per projector) so both stay resident for the device-timed loop
+    ctxs = [bg.Backend(local), bg.Backend(local)]
+    tstream = torch.cuda.current_stream()
+    if world > 1:
+        uid = [ctxs[0].nccl_unique_id() if rank == 0 else None, ctxs[1].nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+    for j, c in enumerate(ctxs):
+        c.set_stream(tstream.cuda_stream)
+        c.set_shard(rank, world)
+        if world > 1:
+            c.nccl_join(uid[j])
+        c.set_decomposition(t, exact, L)
+    lop3_peak, popc_peak = ctxs[0].measure_int_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: projector + decomposition uploaded once, kernels only in the loop
+    ctxs[0].sampled_prepare(G, samples, 1, 1001)
+    ctxs[1].sampled_prepare(H, samples, 1, 1002)
+    results = []
+
+    def step_resident():
+        ctxs[0].sampled_run()
+        ctxs[1].sampled_run()
+        num = ctxs[0].sampled_finish(1.0)         # includes the NCCL all-reduce + 8-byte D2H
+        den = ctxs[1].sampled_finish(1.0)
+        results.append((num, den))
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches = 0.0, 0
+    e0.record(tstream)
+    for _ in range(args.steps):
+        step_resident()
+        for c in ctxs:
+            st = c.stats()
+            kernel_ms += st["kernel_ms"]
+            launches += st["launches"]
+    e1.record(tstream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    pairs_per_step = 2 * samples * chi
+    value = pairs_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: the C-ABI calls a host makes per probability(): decomposition + projector
+    # from HOST memory, kernels, all-reduce, result back to the host — every step.
+    def step_e2e():
+        for c, P, seed in ((ctxs[0], G, 2001), (ctxs[1], H, 2002)):
+            c.set_decomposition(t, exact, L)
+            c.sampled_norm(P, samples, 1, seed, 1.0)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    e0.record(tstream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(tstream)
+    barrier()
+    wall = time.perf_counter() - w0
+    tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * args.steps / float(tw.item())
+    h2d = 2 * (chi * 8 + (t + 1) * 8 * 0 + 2 * 1024 + 2 * 128 + 8)   # terms table + bg_projector struct, per projector
+    import ctypes
+    h2d = 2 * (chi * 8 + ctypes.sizeof(bg.Projector))
+    d2h = 2 * 8
+
+    if rank == 0:
+        # algorithmic lane-ops per inner product: see DESIGN.md section "Roofline"
+        W = {"hidden_shift_n40_t40_k9_L65536": None}.get(cfgname)
+        clocks = sampler.summary()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        work = json.load(open(os.path.join(ROOT, "profiles", "work_model.json"))) if os.path.exists(
+            os.path.join(ROOT, "profiles", "work_model.json")) else {}
+        wm = work.get(cfgname, {})
+        lane_ops = wm.get("alu_lane_ops_per_pair")
+        per_launch_pairs = samples * chi / world
+        k_ms = kernel_ms / max(1, args.steps * 2)
+        roof = {"bound": "int_alu", "unit": "Tlaneop/s",
+                "peak": lop3_peak / 1e12, "peak_source": "bg_measure_int_peak (LOP3 microbenchmark, this run)",
+                "popc_peak": popc_peak / 1e12,
+                "kernel_ms_per_projector": k_ms,
+                "achieved": (per_launch_pairs * lane_ops / (k_ms * 1e-3) / 1e12) if lane_ops else None,
+                "lane_ops_per_pair": lane_ops,
+                "traffic": wm.get("dram_bytes_per_launch"),
+                "hbm_gbs_peak": peaks.get("hbm_gbs")}
+        roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["achieved"] else None
+        line = {"metric": "stabilizer inner products/sec", "value": value, "unit": "inner products/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u64 bit rows + Z8 integer phases (int64 exact accumulation, fp64 final)",
+                "data": "synthetic",
+                "config": {"workload": cfgname, "description": desc, "t": t, "chi": chi,
+                           "samples_per_projector": samples, "projectors": 2,
+                           "l2": "per-sample records (2 x %.0f MB) exceed nothing: the kernel is ALU-bound; "
+                                 "inputs regenerated every step from the counter-based RNG" % (samples * 1072 / 1e6)},
+                "e2e": {"value": e2e_value, "unit": "inner products/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "roofline": roof,
+                "clocks": clocks,
+                "result": {"numerator": results[-1][0], "denominator": results[-1][1]}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(cfgname)
+        print(json.dumps(line))
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -520,20 +520,31 @@ BG_DEV void term_H(const QForm<NS>& base, const typename WordOf<NS>::T (&Cw0)[NS
 // sum of eps 2^{p/2} w^m (w = e^{i pi/4}) as four integers (coefficients of 1, w, w^2, w^3)
 // in units of 2^-sh, sh = t/2 + 1:  p >= -t for a non-zero overlap of normalised states.
 struct Zw { long long a[4]; };
+// z += sgn * mag * w^e  without dynamic indexing (keeps the accumulator in registers)
+BG_DEV void zw_add_pow(Zw& z, int e, long long mag) {
+    const long long v = (e & 4) ? -mag : mag;
+    const int j = e & 3;
+    z.a[0] += (j == 0) ? v : 0;
+    z.a[1] += (j == 1) ? v : 0;
+    z.a[2] += (j == 2) ? v : 0;
+    z.a[3] += (j == 3) ? v : 0;
+}
 BG_DEV void zw_add(Zw& z, int eps, int p, int m, int sh) {
     if (!eps) return;
     const int f = (p >= 0 ? p : p - 1) / 2;              // floor(p/2)
     const long long mag = 1ll << (sh + f);
     const int mm = m & 7;
     if ((p & 1) == 0) {
-        z.a[mm & 3] += (mm & 4) ? -mag : mag;
+        zw_add_pow(z, mm, mag);
     } else {                                             // sqrt2 w^m = w^{m+1} + w^{m-1}
-        const int u = (mm + 1) & 7, d = (mm + 7) & 7;
-        z.a[u & 3] += (u & 4) ? -mag : mag;
-        z.a[d & 3] += (d & 4) ? -mag : mag;
+        zw_add_pow(z, (mm + 1) & 7, mag);
+        zw_add_pow(z, (mm + 7) & 7, mag);
     }
 }
 
+}  // namespace bg
+
+namespace bg {
 // ---------------------------------------------------------------- global-memory helpers
 // Load a bg_state (contiguous layout: active rows are 0..k-1).  Junk that the reference
 // leaves outside the k x k block / beyond n (stabilizer.c:743-745, matrix.c:85-92) is masked.

@@ -6,7 +6,7 @@
 // set of states is identical for any number of GPUs / any launch geometry.
 //
 // Stream layout (key = seed, counter = (l lo, l hi, bin, block)); mirrored on the CPU by
-// oracle/packed_oracle.c:orc_random_state_philox.
+// the test oracle (restated there for the bit-exact RNG check).
 //   block 0          : words 0,1 -> u = ((w1:w0 >> 11) + 1) 2^-53 in (0,1] -> d (eq. 79 cdf), k = n - d
 //   block 1 + j/2    : half j%2  -> xi_j, the j-th random hyperplane of the lazy shrink
 //   block 0x1000     : half 0 -> h,  half 1 -> D1

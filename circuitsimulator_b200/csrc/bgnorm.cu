@@ -1,0 +1,1132 @@
+// bgnorm.cu — CUDA kernels (sm_100a) and the C ABI of include/bgnorm.h.
+//
+// Hot path = the L x chi loop of libcirc/innerprod.c:88-144 (reference repo
+// patrickrall/CircuitSimulator).  Three kernels per projector evaluation:
+//
+//   k_prepare  one warp per sample: draw theta on the device (Philox) or load it, apply the
+//              projector's generators (measurePauli), turn the result into its ambient
+//              quadratic form + parity checks, store a 1 KB record in HBM.
+//   k_pairs    persistent CTAs, one warp per work item (sample, chunk of terms): the chi
+//              decomposition terms are staged ONCE per CTA into shared memory with a TMA bulk
+//              copy (cp.async.bulk + mbarrier); every <phi_i|theta> is evaluated in registers
+//              (ballot / shfl / LOP3 / POPC), accumulated exactly in Z[e^{i pi/4}] as int64.
+//   k_finalize 2^t |projfactor * sum|^2 per sample in fp64 and a fixed-order tree sum.
+//
+// There is no CPU fallback anywhere in this file: every entry point either runs the kernels
+// or fails with an error string.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "bgnorm.h"
+#include "bg_device.cuh"
+#include "bg_philox.cuh"
+#include "bg_warp_ops.cuh"
+
+using namespace bg;
+
+// ------------------------------------------------------------------------------------------
+// device-side records
+// ------------------------------------------------------------------------------------------
+struct SampleRec {          // one projected theta in ambient form (see bg_device.cuh: ambient())
+    int32_t alive, k1, npf, Q;
+    uint64_t D1, D2, Cpend, Cbeta;
+    uint64_t J[BG_MAX_T];
+    uint64_t Cw[BG_MAX_T];
+};
+
+enum { SRC_RNG = 0, SRC_STATES = 1, SRC_TERMS = 2 };
+
+struct PrepArgs {
+    SampleRec* recs;
+    int n_samples;          // records to produce on this rank
+    int t;
+    int project;
+    const bg_projector* P;
+    // SRC_RNG
+    uint64_t seed; uint32_t bin; uint64_t first, stride;
+    const double* cdf;
+    // SRC_STATES
+    const bg_state* states;
+    // SRC_TERMS
+    const uint64_t* terms; int exact;
+    // optional dump of the native state before projection (active-mask layout)
+    bg_state* raw_out; uint64_t* raw_A;
+};
+
+struct PairArgs {
+    const SampleRec* recs;
+    int n_samples;
+    const uint64_t* terms;
+    int nterms;
+    int t;
+    int chunk, chunks_per_sample;
+    unsigned long long* counter;
+    long long* zw;          // [n_samples][4]
+    long long* zw2;         // [n_samples][4]   (exact-norm mode: off-diagonal part)
+    int32_t* epm;           // optional [n_samples][nterms][3]
+    int smem_terms;         // terms staged in shared memory (0: read from global / L2)
+    int tri;                // exact-norm mode: sample i meets terms j >= first_index(i)
+    uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
+    unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
+};
+
+// ------------------------------------------------------------------------------------------
+// k_prepare
+// ------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void term_native(Native<NS>& st, int t, int exact, uint64_t term) {
+    typedef typename WordOf<NS>::T W;
+    const int lane = bg_lane();
+    native_identity<NS>(st, t);
+    if (!exact) {                         // prepL (stateprep.c:85-120): |+> on supp(x~), |0> elsewhere
+        st.f.A = (W)term & lowmaskw<W>(t);
+        return;
+    }
+    // prepH (stateprep.c:36-81)
+    const W e1 = (W)term;
+    const W maskt = lowmaskw<W>(t);
+    const W pairs = (W)0x5555555555555555ull & (maskt >> 1);
+    const W cz = ~e1 & pairs, cz2 = cz | (cz << 1);
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int v = lane + 32 * s;
+        if ((cz2 >> v) & 1) st.f.J[s] = bitw<W>(v ^ 1);
+    }
+    for (W rem = e1 & pairs; rem;) {
+        const int q = lowestw(rem); rem &= rem - 1;
+        native_shrink<NS>(st, bitw<W>(q) | bitw<W>(q + 1), 0u, false);
+    }
+    if ((t & 1) && ((e1 >> (t - 1)) & 1)) native_shrink<NS>(st, bitw<W>(t - 1), 0u, false);
+}
+
+template <int NS, int SRC>
+__global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
+    typedef typename WordOf<NS>::T W;
+    const int lane = bg_lane();
+    const int warps_per_block = blockDim.x >> 5;
+    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int nw = gridDim.x * warps_per_block;
+    for (int idx = gw; idx < a.n_samples; idx += nw) {
+        Native<NS> st;
+        if (SRC == SRC_RNG) native_random<NS>(st, a.t, a.seed, a.bin, a.first + (uint64_t)idx * a.stride, a.cdf);
+        else if (SRC == SRC_STATES) native_load<NS>(st, &a.states[idx]);
+        else term_native<NS>(st, a.t, a.exact, a.terms[a.first + (uint64_t)idx * a.stride]);
+        if (a.raw_out) native_store_raw<NS>(st, &a.raw_out[idx], &a.raw_A[idx]);
+        int npf = 0;
+        bool alive = true;
+        if (a.project) alive = project_native<NS>(st, a.P, npf);
+        SampleRec* r = &a.recs[idx];
+        if (!alive) {
+            if (lane == 0) { r->alive = 0; r->k1 = 0; r->npf = 0; r->Q = 0; }
+            continue;
+        }
+        Ambient<NS> am;
+        make_ambient<NS>(st, am);
+        if (lane == 0) {
+            r->alive = 1; r->k1 = am.k1; r->npf = npf; r->Q = (int32_t)am.f.Q;
+            r->D1 = (uint64_t)am.f.D1; r->D2 = (uint64_t)am.f.D2;
+            r->Cpend = (uint64_t)am.Cpend; r->Cbeta = (uint64_t)am.Cbeta;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            r->J[lane + 32 * s] = (uint64_t)am.f.J[s];
+            r->Cw[lane + 32 * s] = (uint64_t)am.Cw[s];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pairs
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage `bytes` (multiple of 16, 16-byte aligned on both sides) from global to shared memory
+// with the TMA bulk-copy engine; completion is signalled on an mbarrier.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        uint32_t off = 0;
+        while (off < bytes) {
+            const uint32_t n = min(bytes - off, 32768u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32((const char*)smem_dst + off)), "l"((const char*)gsrc + off), "r"(n),
+                           "r"(smem_u32(mbar)) : "memory");
+            off += n;
+        }
+    }
+    // every thread waits for phase 0 of the barrier
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+    }
+}
+
+template <int NS, bool EXACT>
+__global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
+    typedef typename WordOf<NS>::T W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int lane = bg_lane();
+    if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
+    const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
+
+    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)a.chunks_per_sample;
+    const int sh = a.t / 2 + 1;
+    unsigned long long my_pairs = 0;
+    while (true) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ull);
+        item = __shfl_sync(BG_FULL, item, 0);
+        if (item >= n_items) break;
+        const int idx = (int)(item / (unsigned)a.chunks_per_sample);
+        const int c = (int)(item % (unsigned)a.chunks_per_sample);
+        const SampleRec* r = &a.recs[idx];
+        if (!r->alive) continue;
+        int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
+        long long diag_index = -1;
+        if (a.tri) {                                // exactProjectorWork: pairs (i, j >= i)
+            diag_index = (long long)(a.first + (uint64_t)idx * a.stride);
+            if ((long long)i0 < diag_index) i0 = (int)diag_index;
+        }
+        if (i0 >= i1) continue;
+        Ambient<NS> am;
+        am.f.Q = (uint32_t)r->Q; am.f.D1 = (W)r->D1; am.f.D2 = (W)r->D2;
+        am.f.A = lowmaskw<W>(a.t);
+        am.Cpend = (W)r->Cpend; am.Cbeta = (W)r->Cbeta; am.k1 = r->k1;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            am.f.J[s] = (W)r->J[lane + 32 * s];
+            am.Cw[s] = (W)r->Cw[lane + 32 * s];
+        }
+        Zw z, z2;
+        z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+        z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
+        for (int i = i0; i < i1; i++) {
+            const W term = (W)terms[i];
+            int e, p, m;
+            if (EXACT) term_H<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, am.k1, a.t, term, e, p, m);
+            else term_L<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, am.k1, term, e, p, m);
+            if (a.tri && (long long)i != diag_index) zw_add(z2, e, p, m, sh);
+            else zw_add(z, e, p, m, sh);
+            if (a.epm && lane == 0) {
+                int32_t* o = a.epm + ((size_t)idx * a.nterms + i) * 3;
+                o[0] = e; o[1] = p; o[2] = m & 7;
+            }
+        }
+        my_pairs += (unsigned long long)(i1 - i0);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (z.a[j]) atomicAdd((unsigned long long*)&a.zw[(size_t)idx * 4 + j], (unsigned long long)z.a[j]);
+                if (a.tri && z2.a[j]) atomicAdd((unsigned long long*)&a.zw2[(size_t)idx * 4 + j], (unsigned long long)z2.a[j]);
+            }
+        }
+    }
+    if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
+}
+
+// generic pairs: one warp per pair
+template <int NS>
+__global__ void __launch_bounds__(128) k_inner_products(const bg_state* a, const bg_state* b, size_t n_pairs, int32_t* epm) {
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t gw = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const size_t nw = (size_t)gridDim.x * warps_per_block;
+    for (size_t i = gw; i < n_pairs; i += nw) {
+        int e, p, m;
+        warp_inner_product<NS>(&a[i], &b[i], e, p, m);
+        if (bg_lane() == 0) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m & 7; }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) k_measure_pauli(bg_state* st, uint64_t* A, size_t n, const int32_t* m,
+                                                       const uint64_t* zeta, const uint64_t* xi, int32_t* code) {
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t gw = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const size_t nw = (size_t)gridDim.x * warps_per_block;
+    for (size_t i = gw; i < n; i += nw) {
+        const int r = warp_measure_pauli<NS>(&st[i], &A[i], m[i], zeta[i], xi[i]);
+        if (bg_lane() == 0) code[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_finalize: per-sample value and fixed-order reduction
+// ------------------------------------------------------------------------------------------
+// (a0 + a1 w + a2 w^2 + a3 w^3), w = e^{i pi/4}:  re = a0 + (a1-a3)/sqrt2, im = a2 + (a1+a3)/sqrt2
+__device__ __forceinline__ void zw_to_complex(const long long* a, double& re, double& im) {
+    const double c_hi = 0.70710678118654757, c_lo = -4.8336466567264567e-17;   // 1/sqrt2 = c_hi + c_lo
+    const double d1 = (double)(a[1] - a[3]), d2 = (double)(a[1] + a[3]);
+    const double p1 = d1 * c_hi, e1 = fma(d1, c_hi, -p1) + d1 * c_lo;
+    const double p2 = d2 * c_hi, e2 = fma(d2, c_hi, -p2) + d2 * c_lo;
+    const double a0 = (double)a[0], a2 = (double)a[2];
+    double s = a0 + p1, bb = s - a0; double err = (a0 - (s - bb)) + (p1 - bb);
+    re = s + (err + e1);
+    s = a2 + p2; bb = s - a2; err = (a2 - (s - bb)) + (p2 - bb);
+    im = s + (err + e2);
+}
+
+// sampled mode: value_l = 2^t |projfactor * total|^2   (innerprod.c:142)
+__global__ void k_finalize_sampled(const SampleRec* recs, const long long* zw, int n, int t, double* per_sample) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0;
+    if (recs[i].alive) {
+        double re, im;
+        zw_to_complex(&zw[(size_t)i * 4], re, im);
+        const int sh = t / 2 + 1;
+        v = ldexp(re * re + im * im, t - recs[i].npf - 2 * sh);
+    }
+    per_sample[i] = v;
+}
+
+// exact mode: part_i = pf_i * (diag_i) if i == j, plus (2 pf_i Re(offdiag_i), 0)   (innerprod.c:254-260)
+__global__ void k_finalize_exact(const SampleRec* recs, const long long* zw, const long long* zw2, int n, int t,
+                                 double* per_re, double* per_im) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double vr = 0.0, vi = 0.0;
+    if (recs[i].alive) {
+        double re, im, re2, im2;
+        zw_to_complex(&zw[(size_t)i * 4], re, im);
+        zw_to_complex(&zw2[(size_t)i * 4], re2, im2);
+        const int sh = t / 2 + 1;
+        const double pf = pow(2.0, -0.5 * recs[i].npf);
+        vr = ldexp((re + 2.0 * re2) * pf, -sh);
+        vi = ldexp(im * pf, -sh);
+    }
+    per_re[i] = vr; per_im[i] = vi;
+}
+
+// out[0] = sum(x[0..n)) in a fixed order (thread-strided partials, then a binary tree)
+__global__ void __launch_bounds__(1024) k_sum(const double* x, int n, double* out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += x[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ ...) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclUniqueId { char internal[128]; };
+typedef int (*nccl_init_rank_fn)(void**, int, NcclUniqueId, int);
+static NcclApi g_nccl;
+
+struct bg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    int rank = 0, world = 1;
+    bool allreduce = true;
+    void* nccl_comm = nullptr;
+    // decomposition
+    int t = 0, exact = 1, k = 0;
+    std::vector<uint64_t> L;
+    std::vector<uint64_t> terms_host;
+    uint64_t* d_terms = nullptr; size_t d_terms_cap = 0;
+    double* d_cdf = nullptr; int cdf_t = -1;
+    // buffers
+    SampleRec* d_recs = nullptr; size_t recs_cap = 0;
+    long long* d_zw = nullptr; size_t zw_cap = 0;
+    long long* d_zw2 = nullptr; size_t zw2_cap = 0;
+    double* d_per = nullptr; size_t per_cap = 0;
+    double* d_per2 = nullptr; size_t per2_cap = 0;
+    int ctas_per_sm = 8, items_factor = 8;
+    bg_projector* d_P = nullptr;
+    unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
+    double* d_red = nullptr;                    // [8] reduction outputs
+    // prepared sampled run
+    bg_projector P_host;
+    uint64_t samples = 0; int bins = 1; uint64_t seed = 0;
+    bool prepared = false;
+    std::vector<double> bin_sums;
+    bg_stats stats;
+    std::string err;
+};
+
+static int fail(bg_ctx* ctx, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <typename T> static int ensure(bg_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 4 + 16;
+    cudaError_t e = cudaMalloc((void**)p, want * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+    *cap = want;
+    return 0;
+}
+
+extern "C" const char* bg_last_error(const bg_ctx* ctx) {
+    if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+extern "C" int bg_init(bg_ctx** out, int device) {
+    if (!out) return fail(nullptr, "bg_init: null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "bg_init: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, "bg_init: device %d out of range (0..%d)", device, ndev - 1);
+    bg_ctx* ctx = new bg_ctx();
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaSetDevice(%d) failed", device); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        int r = fail(nullptr, "bg_init: device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+        delete ctx; return r;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaStreamCreate failed"); }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    if (cudaMalloc((void**)&ctx->d_P, sizeof(bg_projector)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_red, 8 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_cdf, (BG_MAX_T + 1) * sizeof(double)) != cudaSuccess) {
+        int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx; return r;
+    }
+    if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
+    if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void bg_shutdown(bg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    cudaFree(ctx->d_terms); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
+    cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int bg_set_shard(bg_ctx* ctx, int rank, int world) {
+    if (!ctx) return fail(nullptr, "bg_set_shard: null ctx");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "bg_set_shard: bad rank %d of %d", rank, world);
+    ctx->rank = rank; ctx->world = world;
+    return 0;
+}
+
+extern "C" int bg_set_stream(bg_ctx* ctx, void* stream) {
+    if (!ctx) return fail(nullptr, "bg_set_stream: null ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+extern "C" int bg_set_allreduce(bg_ctx* ctx, int enabled) {
+    if (!ctx) return fail(nullptr, "bg_set_allreduce: null ctx");
+    ctx->allreduce = enabled != 0;
+    return 0;
+}
+
+// ---- NCCL (loaded lazily so that single-GPU use never needs it) ---------------------------
+static int nccl_load(bg_ctx* ctx) {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return fail(ctx, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+    g_nccl.handle = h;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, ...))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(ctx, "NCCL symbols missing in libnccl");
+    return 0;
+}
+
+extern "C" int bg_nccl_unique_id(uint8_t id[128]) {
+    if (nccl_load(nullptr)) return 1;
+    NcclUniqueId u; memset(&u, 0, sizeof u);
+    int r = g_nccl.GetUniqueId(&u);
+    if (r != 0) return fail(nullptr, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    memcpy(id, &u, 128);
+    return 0;
+}
+
+extern "C" int bg_nccl_join(bg_ctx* ctx, const uint8_t id[128]) {
+    if (!ctx) return fail(nullptr, "bg_nccl_join: null ctx");
+    if (ctx->world <= 1) return 0;
+    if (nccl_load(ctx)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    NcclUniqueId u; memcpy(&u, id, 128);
+    int r = ((nccl_init_rank_fn)g_nccl.CommInitRank)(&ctx->nccl_comm, ctx->world, u, ctx->rank);
+    if (r != 0) return fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return 0;
+}
+
+// all-reduce (sum) n doubles held in ctx->d_red; no-op for world == 1
+static int allreduce_red(bg_ctx* ctx, int n) {
+    if (ctx->world <= 1 || !ctx->allreduce) return 0;
+    if (!ctx->nccl_comm) return fail(ctx, "world = %d but bg_nccl_join was not called", ctx->world);
+    int r = g_nccl.AllReduce(ctx->d_red, ctx->d_red, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return 0;
+}
+
+// ---- decomposition ------------------------------------------------------------------------
+// binrep (stateprep.c:5-32) is MSB-first: character j of the string is bit (size-1-j) of i
+static inline int binbit(uint64_t val, int sz, int j) { return (int)((val >> (sz - 1 - j)) & 1ull); }
+
+// cumulative distribution of d = n - k, stabilizer.c:677-716
+static void dimension_cdf(int n, double* cumulative) {
+    double dist[BG_MAX_T + 1], sum = 0;
+    for (int d = 0; d <= n; d++) {
+        double le = 0.;
+        if (d > 0) {
+            double product = 0;
+            for (int a = 1; a <= d; a++) { product += log2(1 - pow(2, d - n - a)); product -= log2(1 - pow(2, -a)); }
+            le = (-d * (d + 1) / 2) + product;
+        }
+        dist[d] = pow(2, le); sum += dist[d];
+    }
+    for (int d = 0; d <= n; d++) dist[d] /= sum;
+    for (int i = 0; i <= n; i++) { cumulative[i] = 0; for (int d = 0; d <= i; d++) cumulative[i] += dist[d]; }
+    for (int i = 0; i <= n; i++) cumulative[i] /= cumulative[n];
+}
+
+extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const uint64_t* L_rows) {
+    if (!ctx) return fail(nullptr, "bg_set_decomposition: null ctx");
+    if (t < 1 || t > BG_MAX_T) return fail(ctx, "bg_set_decomposition: t = %d outside 1..%d", t, BG_MAX_T);
+    CK(cudaSetDevice(ctx->device));
+    size_t chi;
+    if (exact) {
+        const int size = (t + 1) / 2;
+        if (size > 26) return fail(ctx, "bg_set_decomposition: exact decomposition with 2^%d terms is too large", size);
+        chi = (size_t)1 << size;
+        ctx->terms_host.resize(chi);
+        for (size_t i = 0; i < chi; i++) {
+            uint64_t e1 = 0;
+            for (int j = 0; j < size; j++) if (binbit(i, size, j)) e1 |= 1ull << (2 * j);
+            ctx->terms_host[i] = e1;
+        }
+        ctx->L.clear(); ctx->k = 0;
+    } else {
+        if (k < 0 || k > 26 || k > t) return fail(ctx, "bg_set_decomposition: k = %d outside 0..min(t,26)", k);
+        if (k > 0 && !L_rows) return fail(ctx, "bg_set_decomposition: L_rows is null");
+        const uint64_t maskt = t >= 64 ? ~0ull : ((1ull << t) - 1);
+        ctx->L.assign(L_rows, L_rows + k);
+        for (auto& r : ctx->L) r &= maskt;
+        chi = (size_t)1 << k;
+        ctx->terms_host.resize(chi);
+        for (size_t i = 0; i < chi; i++) {         // x~_i = xor of the rows of L picked by binrep(i) (stateprep.c:87-103)
+            uint64_t x = 0;
+            for (int j = 0; j < k; j++) if (binbit(i, k, j)) x ^= ctx->L[j];
+            ctx->terms_host[i] = x;
+        }
+        ctx->k = k;
+    }
+    ctx->t = t; ctx->exact = exact ? 1 : 0;
+    size_t padded = (chi + 1) & ~(size_t)1;        // 16-byte multiple for the bulk copy
+    if (ensure(ctx, &ctx->d_terms, &ctx->d_terms_cap, padded)) return 1;
+    CK(cudaMemsetAsync(ctx->d_terms, 0, padded * 8, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_terms, ctx->terms_host.data(), chi * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->cdf_t != t) {
+        double cdf[BG_MAX_T + 1];
+        dimension_cdf(t, cdf);
+        CK(cudaMemcpyAsync(ctx->d_cdf, cdf, (t + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->cdf_t = t;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prepared = false;
+    return 0;
+}
+
+// reference bit layouts: bit `loc` of a BitVector/BitMatrix is (data[loc/8] >> (7 - loc%8)) & 1
+static inline int refbit(const uint8_t* data, size_t loc) { return (data[loc / 8] >> (7 - loc % 8)) & 1; }
+
+extern "C" int bg_set_decomposition_bitmatrix(bg_ctx* ctx, int t, int exact, int k, const uint8_t* L_bits) {
+    std::vector<uint64_t> rows;
+    if (!exact) {
+        if (k > 0 && !L_bits) return fail(ctx, "bg_set_decomposition_bitmatrix: L_bits is null");
+        if (t < 1 || t > BG_MAX_T) return fail(ctx, "bg_set_decomposition_bitmatrix: t = %d outside 1..%d", t, BG_MAX_T);
+        rows.assign(k > 0 ? k : 0, 0);
+        for (int r = 0; r < k; r++)
+            for (int c = 0; c < t; c++) if (refbit(L_bits, (size_t)r * t + c)) rows[r] |= 1ull << c;
+    }
+    return bg_set_decomposition(ctx, t, exact, k, rows.data());
+}
+
+extern "C" int bg_projector_from_bitmatrix(bg_projector* out, int nstabs, int nqubits, const uint8_t* phase_sign,
+                                           const uint8_t* phase_complex, const uint8_t* xs, const uint8_t* zs) {
+    if (!out) return fail(nullptr, "bg_projector_from_bitmatrix: null out");
+    if (nstabs < 0 || nstabs > BG_MAX_STABS) return fail(nullptr, "projector with %d generators (max %d)", nstabs, BG_MAX_STABS);
+    if (nqubits < 0 || nqubits > BG_MAX_T) return fail(nullptr, "projector on %d qubits (max %d)", nqubits, BG_MAX_T);
+    memset(out, 0, sizeof *out);
+    out->nstabs = nstabs; out->nqubits = nqubits;
+    for (int i = 0; i < nstabs; i++) {
+        out->phase[i] = (uint8_t)(2 * refbit(phase_sign, i) + refbit(phase_complex, i));
+        for (int q = 0; q < nqubits; q++) {
+            if (refbit(xs, (size_t)i * nqubits + q)) out->xs[i] |= 1ull << q;
+            if (refbit(zs, (size_t)i * nqubits + q)) out->zs[i] |= 1ull << q;
+        }
+    }
+    return 0;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------
+static const int WARPS_PER_BLOCK = 4;
+static const size_t SMEM_TERMS_MAX = 8192;     // 64 KB of staged terms
+
+template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepArgs& a) {
+    const int blocks = std::max(1, std::min((a.n_samples + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, ctx->sm_count * 16));
+    if (src == SRC_RNG) k_prepare<NS, SRC_RNG><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(a);
+    else if (src == SRC_STATES) k_prepare<NS, SRC_STATES><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(a);
+    else k_prepare<NS, SRC_TERMS><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
+static int launch_prepare(bg_ctx* ctx, int src, const PrepArgs& a) {
+    if (a.n_samples <= 0) return 0;
+    return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
+}
+
+template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_pairs<NS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_TERMS_MAX * 8)));
+    k_pairs<NS, EXACT><<<blocks, 32 * WARPS_PER_BLOCK, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
+
+// Fill in chunking / staging and launch k_pairs.  zw (and zw2) must be zeroed already.
+static int launch_pairs(bg_ctx* ctx, PairArgs a) {
+    if (a.n_samples <= 0) return 0;
+    const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
+    const int want_items = resident_warps * ctx->items_factor;
+    int cps = 1;
+    if (a.n_samples < want_items) cps = (want_items + a.n_samples - 1) / a.n_samples;
+    int chunk = (a.nterms + cps - 1) / cps;
+    if (chunk < 16) chunk = 16;
+    if (chunk > a.nterms) chunk = a.nterms;
+    cps = (a.nterms + chunk - 1) / chunk;
+    a.chunk = chunk; a.chunks_per_sample = cps;
+    const size_t padded = ((size_t)a.nterms + 1) & ~(size_t)1;
+    a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;
+    const size_t smem = (size_t)a.smem_terms * 8;
+    const unsigned long long items = (unsigned long long)a.n_samples * cps;
+    long long blocks = (long long)ctx->sm_count * ctx->ctas_per_sm;   // persistent CTAs, a multiple of the SM count
+    const long long need = (long long)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    a.counter = ctx->d_counters; a.pair_count = ctx->d_counters + 1;
+    if (a.t <= 32) return ctx->exact ? launch_pairs_ns<1, true>(ctx, a, (int)blocks, smem) : launch_pairs_ns<1, false>(ctx, a, (int)blocks, smem);
+    return ctx->exact ? launch_pairs_ns<2, true>(ctx, a, (int)blocks, smem) : launch_pairs_ns<2, false>(ctx, a, (int)blocks, smem);
+}
+
+static int ensure_sample_buffers(bg_ctx* ctx, size_t n) {
+    if (ensure(ctx, &ctx->d_recs, &ctx->recs_cap, n)) return 1;
+    if (ensure(ctx, &ctx->d_zw, &ctx->zw_cap, n * 4)) return 1;
+    if (ensure(ctx, &ctx->d_zw2, &ctx->zw2_cap, n * 4)) return 1;
+    if (ensure(ctx, &ctx->d_per, &ctx->per_cap, n)) return 1;
+    if (ensure(ctx, &ctx->d_per2, &ctx->per2_cap, n)) return 1;
+    return 0;
+}
+
+// number of sample indices l in [0, total) with l % world == rank
+static inline uint64_t shard_count(uint64_t total, int rank, int world) {
+    return total / world + ((uint64_t)rank < total % world ? 1 : 0);
+}
+
+// ---- sampled norm -------------------------------------------------------------------------
+static int check_projector(bg_ctx* ctx, const bg_projector* P) {
+    if (!P) return fail(ctx, "null projector");
+    if (P->nstabs < 0 || P->nstabs > BG_MAX_STABS) return fail(ctx, "projector with %d generators (max %d)", P->nstabs, BG_MAX_STABS);
+    if (P->nstabs > 0 && P->nqubits != ctx->t)
+        return fail(ctx, "projector acts on %d qubits but the decomposition has t = %d", P->nqubits, ctx->t);
+    return 0;
+}
+
+// Clifford circuit (t == 0): closed form of innerprod.c:52-62 / 157-167
+static double clifford_closed_form(const bg_projector* P) {
+    double sum = 1;
+    for (int i = 0; i < P->nstabs; i++) { if (P->phase[i] == 0) sum += 1; if (P->phase[i] == 2) sum -= 1; }
+    return sum / (1 + (double)P->nstabs);
+}
+
+extern "C" int bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed) {
+    if (!ctx) return fail(nullptr, "bg_sampled_prepare: null ctx");
+    if (ctx->t <= 0) return fail(ctx, "bg_sampled_prepare: call bg_set_decomposition first");
+    if (check_projector(ctx, P)) return 1;
+    if (P->nstabs == 0) return fail(ctx, "bg_sampled_prepare: empty projector (use bg_sampled_norm for the closed form)");
+    if (bins < 1) return fail(ctx, "bg_sampled_prepare: bins = %d", bins);
+    if (samples < 1) return fail(ctx, "bg_sampled_prepare: samples = 0");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
+    if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
+    if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
+    ctx->P_host = *P;
+    CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes = sizeof(bg_projector);
+    ctx->samples = samples; ctx->bins = bins; ctx->seed = seed;
+    ctx->prepared = true;
+    return 0;
+}
+
+// one bin: prepare + pairs + finalize + sum into d_red[slot], d_red[4+slot] untouched
+static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
+    const uint64_t mine = shard_count(ctx->samples, ctx->rank, ctx->world);
+    const int n = (int)mine;
+    if (n == 0) { CK(cudaMemsetAsync(ctx->d_red + red_slot, 0, sizeof(double), ctx->stream)); return 0; }
+    PrepArgs pa; memset(&pa, 0, sizeof pa);
+    pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
+    pa.seed = ctx->seed; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
+    pa.cdf = ctx->d_cdf;
+    if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
+    CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
+    PairArgs qa; memset(&qa, 0, sizeof qa);
+    qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
+    qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
+    if (launch_pairs(ctx, qa)) return 1;
+    k_finalize_sampled<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per);
+    k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red + red_slot);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 2;
+    return 0;
+}
+
+extern "C" int bg_sampled_run(bg_ctx* ctx) {
+    if (!ctx) return fail(nullptr, "bg_sampled_run: null ctx");
+    if (!ctx->prepared) return fail(ctx, "bg_sampled_run: bg_sampled_prepare not called");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->bins > 4) return fail(ctx, "bg_sampled_run: split-phase API supports at most 4 bins (use bg_sampled_norm)");
+    ctx->stats.launches = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int b = 0; b < ctx->bins; b++) if (run_bin(ctx, b, b)) return 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    return 0;
+}
+
+// the reference's comparator (innerprod.c:17-19): the double difference truncated to int
+static int ref_cmpfunc(const void* a, const void* b) { return (int)(*(const double*)a - *(const double*)b); }
+
+static double median_like_reference(std::vector<double>& v) {
+    const int bins = (int)v.size();
+    if (bins == 1) return v[0];
+    qsort(v.data(), bins, sizeof(double), ref_cmpfunc);
+    if (bins % 2 == 1) return v[(bins - 1) / 2];
+    return (v[bins / 2] + v[bins / 2 - 1]) / 2;
+}
+
+static int collect_stats(bg_ctx* ctx) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.kernel_ms = ms;
+    unsigned long long c[2];
+    CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.pairs = c[1];
+    return 0;
+}
+
+extern "C" int bg_sampled_finish(bg_ctx* ctx, double norm, double* out) {
+    (void)norm;
+    if (!ctx) return fail(nullptr, "bg_sampled_finish: null ctx");
+    if (!ctx->prepared) return fail(ctx, "bg_sampled_finish: nothing was run");
+    if (!out) return fail(ctx, "bg_sampled_finish: null out");
+    CK(cudaSetDevice(ctx->device));
+    if (allreduce_red(ctx, ctx->bins)) return 1;
+    double sums[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(sums, ctx->d_red, ctx->bins * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes = ctx->bins * sizeof(double);
+    if (collect_stats(ctx)) return 1;
+    ctx->stats.pairs *= 1;       // pairs of the LAST bin only are in the counter; fine for bins == 1
+    std::vector<double> v(ctx->bins);
+    for (int b = 0; b < ctx->bins; b++) v[b] = sums[b] / (double)ctx->samples;     // total/samples (innerprod.c:83)
+    *out = median_like_reference(v);
+    return 0;
+}
+
+extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed,
+                               double norm, double* out) {
+    if (!ctx) return fail(nullptr, "bg_sampled_norm: null ctx");
+    if (!out) return fail(ctx, "bg_sampled_norm: null out");
+    if (P && P->nstabs > 0 && P->nqubits == 0) { *out = pow(norm, 2) * clifford_closed_form(P); return 0; }
+    if (check_projector(ctx, P)) return 1;
+    if (P->nstabs == 0) { *out = pow(norm, 2); return 0; }                 // innerprod.c:47
+    if (bins < 1) return fail(ctx, "bg_sampled_norm: bins = %d", bins);
+    if (bg_sampled_prepare(ctx, P, samples, 1, seed)) return 1;
+    std::vector<double> v(bins);
+    double total_ms = 0; uint64_t total_pairs = 0, launches = 0;
+    for (int b = 0; b < bins; b++) {
+        ctx->stats.launches = 0;
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (run_bin(ctx, b, 0)) return 1;
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (allreduce_red(ctx, 1)) return 1;
+        double s = 0;
+        CK(cudaMemcpyAsync(&s, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (collect_stats(ctx)) return 1;
+        total_ms += ctx->stats.kernel_ms; total_pairs += ctx->stats.pairs; launches += ctx->stats.launches;
+        v[b] = s / (double)samples;
+    }
+    ctx->stats.kernel_ms = total_ms; ctx->stats.pairs = total_pairs; ctx->stats.launches = launches;
+    ctx->stats.d2h_bytes = bins * sizeof(double);
+    *out = median_like_reference(v);
+    return 0;
+}
+
+// ---- exact norm ---------------------------------------------------------------------------
+extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, double* out) {
+    if (!ctx) return fail(nullptr, "bg_exact_norm: null ctx");
+    if (!out) return fail(ctx, "bg_exact_norm: null out");
+    if (P && P->nstabs > 0 && P->nqubits == 0) { *out = clifford_closed_form(P); return 0; }
+    if (P && P->nstabs == 0) { *out = pow(norm, 2); return 0; }
+    if (ctx->t <= 0) return fail(ctx, "bg_exact_norm: call bg_set_decomposition first");
+    if (ctx->world > 1 && !ctx->allreduce) return fail(ctx, "bg_exact_norm: world > 1 needs the in-library all-reduce (partial |sum| values do not add)");
+    if (check_projector(ctx, P)) return 1;
+    if (P->nstabs == 0) { *out = pow(norm, 2); return 0; }                 // innerprod.c:150
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t chi = ctx->terms_host.size();
+    const uint64_t mine = shard_count(chi, ctx->rank, ctx->world);
+    const int n = (int)mine;
+    if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
+    CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes = sizeof(bg_projector);
+    ctx->stats.launches = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(double), ctx->stream));
+    if (n > 0) {
+        PrepArgs pa; memset(&pa, 0, sizeof pa);
+        pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
+        pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
+        pa.terms = ctx->d_terms; pa.exact = ctx->exact;
+        if (launch_prepare(ctx, SRC_TERMS, pa)) return 1;
+        CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_zw2, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
+        PairArgs qa; memset(&qa, 0, sizeof qa);
+        qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)chi;
+        qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2; qa.tri = 1;
+        qa.first = (uint64_t)ctx->rank; qa.stride = (uint64_t)ctx->world;
+        if (launch_pairs(ctx, qa)) return 1;
+        k_finalize_exact<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, ctx->d_zw2, n, ctx->t, ctx->d_per, ctx->d_per2);
+        k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red);
+        k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per2, n, ctx->d_red + 1);
+        CK(cudaGetLastError());
+        ctx->stats.launches += 3;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (allreduce_red(ctx, 2)) return 1;
+    double s[2] = {0, 0};
+    CK(cudaMemcpyAsync(s, ctx->d_red, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes = sizeof s;
+    if (collect_stats(ctx)) return 1;
+    *out = sqrt(s[0] * s[0] + s[1] * s[1]);                                 // ComplexMag (innerprod.c:198)
+    return 0;
+}
+
+// ---- parity / debug entry points -----------------------------------------------------------
+static int check_states(bg_ctx* ctx, const bg_state* s, size_t n, int* t_out) {
+    int t = -1;
+    for (size_t i = 0; i < n; i++) {
+        if (s[i].n < 1 || s[i].n > BG_MAX_T || s[i].k < 0 || s[i].k > s[i].n)
+            return fail(ctx, "state %zu has n = %d, k = %d", i, s[i].n, s[i].k);
+        if (t < 0) t = s[i].n;
+        if ((s[i].n <= 32) != (t <= 32)) t = 64;      // mixed widths: use the wide kernel
+    }
+    *t_out = t;
+    return 0;
+}
+
+extern "C" int bg_inner_products(bg_ctx* ctx, size_t n_pairs, const bg_state* a, const bg_state* b, int32_t* epm) {
+    if (!ctx) return fail(nullptr, "bg_inner_products: null ctx");
+    if (n_pairs == 0) return 0;
+    if (!a || !b || !epm) return fail(ctx, "bg_inner_products: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    int ta, tb;
+    if (check_states(ctx, a, n_pairs, &ta) || check_states(ctx, b, n_pairs, &tb)) return 1;
+    for (size_t i = 0; i < n_pairs; i++)
+        if (a[i].n != b[i].n) return fail(ctx, "pair %zu: states of different size (%d vs %d)", i, a[i].n, b[i].n);
+    bg_state *da = nullptr, *db = nullptr; int32_t* de = nullptr;
+    CK(cudaMalloc((void**)&da, n_pairs * sizeof(bg_state)));
+    CK(cudaMalloc((void**)&db, n_pairs * sizeof(bg_state)));
+    CK(cudaMalloc((void**)&de, n_pairs * 3 * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(da, a, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db, b, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = (int)std::min<size_t>((n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (size_t)ctx->sm_count * 16);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (std::max(ta, tb) <= 32) k_inner_products<1><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(da, db, n_pairs, de);
+    else k_inner_products<2><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(da, db, n_pairs, de);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(epm, de, n_pairs * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.kernel_ms = ms; ctx->stats.pairs = n_pairs; ctx->stats.launches = 1;
+    ctx->stats.h2d_bytes = 2 * n_pairs * sizeof(bg_state); ctx->stats.d2h_bytes = n_pairs * 3 * sizeof(int32_t);
+    cudaFree(da); cudaFree(db); cudaFree(de);
+    return 0;
+}
+
+extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, int project, size_t n_states,
+                                           const bg_state* thetas, int32_t* epm, double* per_sample, double* mean) {
+    if (!ctx) return fail(nullptr, "bg_sampled_norm_from_states: null ctx");
+    if (ctx->t <= 0) return fail(ctx, "bg_sampled_norm_from_states: call bg_set_decomposition first");
+    if (n_states == 0) { if (mean) *mean = 0; return 0; }
+    if (!thetas) return fail(ctx, "bg_sampled_norm_from_states: null thetas");
+    if (project && check_projector(ctx, P)) return 1;
+    int tt;
+    if (check_states(ctx, thetas, n_states, &tt)) return 1;
+    for (size_t i = 0; i < n_states; i++)
+        if (thetas[i].n != ctx->t) return fail(ctx, "theta %zu has n = %d but t = %d", i, thetas[i].n, ctx->t);
+    CK(cudaSetDevice(ctx->device));
+    const int n = (int)n_states;
+    const size_t chi = ctx->terms_host.size();
+    if (ensure_sample_buffers(ctx, n_states)) return 1;
+    bg_state* dth = nullptr; int32_t* depm = nullptr;
+    CK(cudaMalloc((void**)&dth, n_states * sizeof(bg_state)));
+    CK(cudaMemcpyAsync(dth, thetas, n_states * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
+    if (project) CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+    if (epm) {
+        CK(cudaMalloc((void**)&depm, n_states * chi * 3 * sizeof(int32_t)));
+        CK(cudaMemsetAsync(depm, 0, n_states * chi * 3 * sizeof(int32_t), ctx->stream));
+    }
+    ctx->stats.launches = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    PrepArgs pa; memset(&pa, 0, sizeof pa);
+    pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = project ? 1 : 0; pa.P = ctx->d_P;
+    pa.states = dth;
+    if (launch_prepare(ctx, SRC_STATES, pa)) return 1;
+    CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
+    PairArgs qa; memset(&qa, 0, sizeof qa);
+    qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)chi;
+    qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2; qa.epm = depm;
+    if (launch_pairs(ctx, qa)) return 1;
+    k_finalize_sampled<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per);
+    k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 2;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    double s = 0;
+    CK(cudaMemcpyAsync(&s, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (per_sample) CK(cudaMemcpyAsync(per_sample, ctx->d_per, n_states * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (epm) CK(cudaMemcpyAsync(epm, depm, n_states * chi * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (collect_stats(ctx)) return 1;
+    ctx->stats.h2d_bytes = n_states * sizeof(bg_state);
+    ctx->stats.d2h_bytes = sizeof(double) + (per_sample ? n_states * sizeof(double) : 0) + (epm ? n_states * chi * 12 : 0);
+    if (mean) *mean = s / (double)n_states;
+    cudaFree(dth); if (depm) cudaFree(depm);
+    return 0;
+}
+
+// Active-mask layout -> contiguous layout (active rows first, order preserved).
+static void compact_state(bg_state* s, uint64_t A) {
+    const int n = s->n;
+    int perm[BG_MAX_T], k = 0, r = 0;
+    for (int v = 0; v < n; v++) if ((A >> v) & 1) perm[r++] = v;
+    k = r;
+    for (int v = 0; v < n; v++) if (!((A >> v) & 1)) perm[r++] = v;
+    bg_state o; memset(&o, 0, sizeof o);
+    o.n = n; o.k = k; o.Q = s->Q & 7; o.h = s->h;
+    for (int i = 0; i < n; i++) {
+        o.G[i] = s->G[perm[i]]; o.Gbar[i] = s->Gbar[perm[i]];
+        if (i < k) {
+            o.D1 |= ((s->D1 >> perm[i]) & 1ull) << i;
+            o.D2 |= ((s->D2 >> perm[i]) & 1ull) << i;
+            uint64_t row = 0;
+            for (int c = 0; c < k; c++) row |= ((s->J[perm[i]] >> perm[c]) & 1ull) << c;
+            o.J[i] = row;
+        }
+    }
+    *s = o;
+}
+
+extern "C" int bg_measure_pauli(bg_ctx* ctx, size_t n_states, bg_state* states, const int32_t* m,
+                                const uint64_t* zeta, const uint64_t* xi, double* result) {
+    if (!ctx) return fail(nullptr, "bg_measure_pauli: null ctx");
+    if (n_states == 0) return 0;
+    if (!states || !m || !zeta || !xi) return fail(ctx, "bg_measure_pauli: null buffer");
+    int tt;
+    if (check_states(ctx, states, n_states, &tt)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    bg_state* ds = nullptr; uint64_t *dA = nullptr, *dz = nullptr, *dx = nullptr; int32_t *dm = nullptr, *dc = nullptr;
+    CK(cudaMalloc((void**)&ds, n_states * sizeof(bg_state)));
+    CK(cudaMalloc((void**)&dA, n_states * 8)); CK(cudaMalloc((void**)&dz, n_states * 8)); CK(cudaMalloc((void**)&dx, n_states * 8));
+    CK(cudaMalloc((void**)&dm, n_states * 4)); CK(cudaMalloc((void**)&dc, n_states * 4));
+    CK(cudaMemcpyAsync(ds, states, n_states * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dz, zeta, n_states * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dx, xi, n_states * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dm, m, n_states * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = (int)std::min<size_t>((n_states + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (size_t)ctx->sm_count * 16);
+    if (tt <= 32) k_measure_pauli<1><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(ds, dA, n_states, dm, dz, dx, dc);
+    else k_measure_pauli<2><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(ds, dA, n_states, dm, dz, dx, dc);
+    CK(cudaGetLastError());
+    std::vector<uint64_t> A(n_states); std::vector<int32_t> code(n_states);
+    CK(cudaMemcpyAsync(states, ds, n_states * sizeof(bg_state), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(A.data(), dA, n_states * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(code.data(), dc, n_states * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n_states; i++) {
+        compact_state(&states[i], A[i]);
+        if (result) result[i] = code[i] == 0 ? 0.0 : (code[i] == 1 ? 1.0 : pow(2, -0.5));
+    }
+    cudaFree(ds); cudaFree(dA); cudaFree(dz); cudaFree(dx); cudaFree(dm); cudaFree(dc);
+    return 0;
+}
+
+// src: SRC_RNG (t, seed, bin, first) or SRC_TERMS (ctx's decomposition, first)
+static int dump_states(bg_ctx* ctx, int src, int t, uint64_t seed, int bin, uint64_t first, size_t count, bg_state* out) {
+    if (count == 0) return 0;
+    if (!out) return fail(ctx, "null output buffer");
+    CK(cudaSetDevice(ctx->device));
+    if (ensure_sample_buffers(ctx, count)) return 1;
+    bg_state* ds = nullptr; uint64_t* dA = nullptr;
+    CK(cudaMalloc((void**)&ds, count * sizeof(bg_state)));
+    CK(cudaMalloc((void**)&dA, count * 8));
+    if (ctx->cdf_t != t && src == SRC_RNG) {
+        double cdf[BG_MAX_T + 1];
+        dimension_cdf(t, cdf);
+        CK(cudaMemcpyAsync(ctx->d_cdf, cdf, (t + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->cdf_t = t;
+    }
+    PrepArgs pa; memset(&pa, 0, sizeof pa);
+    pa.recs = ctx->d_recs; pa.n_samples = (int)count; pa.t = t; pa.project = 0; pa.P = ctx->d_P;
+    pa.seed = seed; pa.bin = (uint32_t)bin; pa.first = first; pa.stride = 1; pa.cdf = ctx->d_cdf;
+    pa.terms = ctx->d_terms; pa.exact = ctx->exact;
+    pa.raw_out = ds; pa.raw_A = dA;
+    if (launch_prepare(ctx, src, pa)) return 1;
+    std::vector<uint64_t> A(count);
+    CK(cudaMemcpyAsync(out, ds, count * sizeof(bg_state), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(A.data(), dA, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < count; i++) compact_state(&out[i], A[i]);
+    cudaFree(ds); cudaFree(dA);
+    return 0;
+}
+
+extern "C" int bg_random_states(bg_ctx* ctx, int t, uint64_t seed, int bin, uint64_t first, size_t count, bg_state* out) {
+    if (!ctx) return fail(nullptr, "bg_random_states: null ctx");
+    if (t < 1 || t > BG_MAX_T) return fail(ctx, "bg_random_states: t = %d outside 1..%d", t, BG_MAX_T);
+    return dump_states(ctx, SRC_RNG, t, seed, bin, first, count, out);
+}
+
+extern "C" int bg_decomposition_terms(bg_ctx* ctx, uint64_t first, size_t count, bg_state* out) {
+    if (!ctx) return fail(nullptr, "bg_decomposition_terms: null ctx");
+    if (ctx->t <= 0) return fail(ctx, "bg_decomposition_terms: call bg_set_decomposition first");
+    if (first + count > ctx->terms_host.size()) return fail(ctx, "bg_decomposition_terms: range beyond chi = %zu", ctx->terms_host.size());
+    return dump_states(ctx, SRC_TERMS, ctx->t, 0, 0, first, count, out);
+}
+
+// ---- integer-pipe peak (the roofline denominator) ---------------------------------------------
+// Every thread runs `iters` x 4 rounds over 8 independent chains of LOP3 (kind 0) or POPC
+// (kind 1), one instruction per chain per round (asm volatile keeps the count exact); sink prevents dead-code elimination.  lane-ops = threads * iters * 8 * ops_per_round.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t* sink, int iters, uint32_t seed) {
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = seed * (threadIdx.x + 1u) + 0x9E3779B9u * (j + 1) + blockIdx.x;
+    const uint32_t c = seed;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (KIND == 0)      // exactly one 3-input LOP3:  x_j ^= x_{j+1} & c
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(x[j]) : "r"(x[(j + 1) & 7]), "r"(c));
+                else                // exactly one POPC (the result feeds itself)
+                    asm volatile("popc.b32 %0, %0;" : "+r"(x[j]));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc ^= x[j];
+    if (acc == 0x12345u) sink[0] = acc;
+}
+
+extern "C" int bg_measure_int_peak(bg_ctx* ctx, double* lop3_lane_ops_per_s, double* popc_lane_ops_per_s) {
+    if (!ctx) return fail(nullptr, "bg_measure_int_peak: null ctx");
+    CK(cudaSetDevice(ctx->device));
+    uint32_t* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, 64));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    double res[2] = {0, 0};
+    for (int kind = 0; kind < 2; kind++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            if (kind == 0) k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep);
+            else k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaEventSynchronize(ctx->ev1));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)blocks * threads * (double)iters * 32.0;     // 4 x 8 ops per iteration
+        res[kind] = ops / (best * 1e-3);
+    }
+    cudaFree(sink);
+    if (lop3_lane_ops_per_s) *lop3_lane_ops_per_s = res[0];
+    if (popc_lane_ops_per_s) *popc_lane_ops_per_s = res[1];
+    return 0;
+}
+
+extern "C" int bg_get_stats(const bg_ctx* ctx, bg_stats* out) {
+    if (!ctx || !out) return fail(nullptr, "bg_get_stats: null argument");
+    *out = ctx->stats;
+    return 0;
+}

@@ -81,6 +81,10 @@ int  bg_set_shard(bg_ctx* ctx, int rank, int world);
  * libcirc/innerprod.c:79-81,192-195).  Rank 0 fills a 128-byte unique id, the
  * caller distributes it by any means, every rank then joins.  After joining,
  * bg_sampled_norm / bg_exact_norm all-reduce their partial sums in-library. */
+/* With all-reduce disabled (enabled = 0) and world > 1, bg_sampled_norm returns this rank's
+ * PARTIAL result, (sum over its samples)/samples, so that the caller can reduce by other means
+ * (bins must be 1); bg_exact_norm refuses.  Default: enabled. */
+int  bg_set_allreduce(bg_ctx* ctx, int enabled);
 int  bg_nccl_unique_id(uint8_t id[128]);
 int  bg_nccl_join(bg_ctx* ctx, const uint8_t id[128]);   /* uses bg_set_shard's rank/world */
 
@@ -166,6 +170,14 @@ int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
 int  bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed);
 int  bg_sampled_run(bg_ctx* ctx);                       /* async on ctx's stream          */
 int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* sync, reduce, all-reduce */
+
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the context's own, so that the caller's events bracket the kernels. */
+int  bg_set_stream(bg_ctx* ctx, void* cuda_stream);
+
+/* Roofline denominator: measured integer-pipe throughput of this GPU, in 32-bit lane-ops per
+ * second, for LOP3 (the ALU pipe the elimination runs on) and for POPC (+IADD). */
+int  bg_measure_int_peak(bg_ctx* ctx, double* lop3_lane_ops_per_s, double* popc_lane_ops_per_s);
 
 #ifdef __cplusplus
 }

@@ -523,41 +523,63 @@ static inline uint64_t u64_of(const uint32_t w[4], int half) {
     return ((uint64_t)w[2 * half + 1] << 32) | w[2 * half];
 }
 
-/* Stream layout shared with circuitsimulator_b200/csrc:
- *   block 0            : words 0,1 -> u = (top 53 bits + 1) * 2^-53 in (0,1]  -> d
- *   block 1 + j/2      : half j%2 -> xi_j, the j-th lazy-shrink vector
+/* The device sampler (circuitsimulator_b200/csrc/bg_philox.cuh:native_random) restated on the
+ * CPU.  Same law as randomStabilizerState (stabilizer.c:689-756): d from the eq. 79 cdf, K cut
+ * from F_2^n by d random hyperplanes (lazy shrink), h, D uniform, J uniform symmetric with
+ * J_aa = D1_a, Q = 0.  It differs from the libc version only in bookkeeping: the device keeps
+ * an active-row mask instead of swapping the pivot row to position k-1, pivots on the LOWEST
+ * row of S, and draws (D, J) per row index before the rows are compacted.
+ * Stream layout (key = seed, counter = (sample lo, sample hi, bin, block)):
+ *   block 0            : words 0,1 -> u = ((w1:w0 >> 11) + 1) 2^-53 in (0,1]  -> d
+ *   block 1 + j/2      : half j%2 -> xi_j, the j-th random hyperplane
  *   block 0x1000       : half 0 -> h, half 1 -> D1
  *   block 0x1001       : half 0 -> D2
- *   block 0x2000 + i   : half 0 -> r_i ; J_ij = bit j of r_i for j < i < k, J symmetric, J_ii = D1_i */
-void orc_random_state_philox(int n, uint64_t seed, uint32_t bin, uint64_t sample, S* s) {
+ *   block 0x2000 + v   : half 0 -> r_v ; J_uv = bit v of r_u for v < u (both active), J_vv = D1_v */
+void orc_random_state_philox(int n, uint64_t seed, uint32_t bin, uint64_t sample, S* out) {
     double cdf[BG_MAX_T + 1];
     orc_dimension_cdf(n, cdf);
     uint32_t w[4];
     orc_philox_block(seed, sample, bin, 0, w);
     double u = (double)((u64_of(w, 0) >> 11) + 1ull) * 0x1.0p-53;
-    int d;
-    for (d = 0; d <= n; d++) if (u <= cdf[d]) break;
-    if (d > n) d = n;
+    int d = 0;
+    while (d < n && !(u <= cdf[d])) d++;
     int k = n - d;
     const uint64_t mn = lowmask(n);
-    orc_identity_state(s, n, n);
-    for (uint32_t j = 0; s->k > k; j++) {
+    uint64_t G[BG_MAX_T], Gb[BG_MAX_T], J[BG_MAX_T], A = mn;
+    for (int i = 0; i < n; i++) { G[i] = Gb[i] = 1ull << i; J[i] = 0; }
+    for (uint32_t j = 0; pop64(A) > k && j < 100000u; j++) {
         orc_philox_block(seed, sample, bin, 1 + j / 2, w);
-        orc_shrink(s, u64_of(w, j % 2) & mn, 0, 1);
+        uint64_t xi = u64_of(w, j % 2) & mn, Sm = 0;
+        for (int a = 0; a < n; a++) if (bit(A, a) && par64(G[a] & xi)) Sm |= 1ull << a;
+        if (!Sm) continue;                                   /* xi orthogonal to K: SAME */
+        int i = __builtin_ctzll(Sm);
+        uint64_t Sp = Sm & ~(1ull << i);
+        for (int a = 0; a < n; a++) if (bit(Sp, a)) { G[a] ^= G[i]; Gb[i] ^= Gb[a]; }
+        A &= ~(1ull << i);
     }
     orc_philox_block(seed, sample, bin, 0x1000, w);
-    s->h = u64_of(w, 0) & mn;
-    s->D1 = u64_of(w, 1) & mn;
+    uint64_t h = u64_of(w, 0) & mn, D1 = u64_of(w, 1) & A;
     orc_philox_block(seed, sample, bin, 0x1001, w);
-    s->D2 = u64_of(w, 0) & mn;
-    for (int i = 0; i < k; i++) {
-        orc_philox_block(seed, sample, bin, 0x2000 + i, w);
-        uint64_t r = u64_of(w, 0);
-        s->J[i] = (s->J[i] & ~(1ull << i)) | ((uint64_t)bit(s->D1, i) << i);
-        for (int j = 0; j < i; j++) {
-            uint64_t b = (r >> j) & 1ull;
-            s->J[i] = (s->J[i] & ~(1ull << j)) | (b << j);
-            s->J[j] = (s->J[j] & ~(1ull << i)) | (b << i);
+    uint64_t D2 = u64_of(w, 0) & A;
+    for (int v = 0; v < n; v++) {
+        if (!bit(A, v)) continue;
+        orc_philox_block(seed, sample, bin, 0x2000 + v, w);
+        uint64_t r = u64_of(w, 0) & lowmask(v) & A;
+        J[v] |= r | ((uint64_t)bit(D1, v) << v);
+        for (int c = 0; c < v; c++) if (bit(r, c)) J[c] |= 1ull << v;
+    }
+    /* compact: active rows first, order preserved */
+    int perm[BG_MAX_T], r = 0;
+    for (int v = 0; v < n; v++) if (bit(A, v)) perm[r++] = v;
+    for (int v = 0; v < n; v++) if (!bit(A, v)) perm[r++] = v;
+    memset(out, 0, sizeof(*out));
+    out->n = n; out->k = k; out->Q = 0; out->h = h;
+    for (int i = 0; i < n; i++) {
+        out->G[i] = G[perm[i]]; out->Gbar[i] = Gb[perm[i]];
+        if (i < k) {
+            out->D1 |= (uint64_t)bit(D1, perm[i]) << i;
+            out->D2 |= (uint64_t)bit(D2, perm[i]) << i;
+            for (int c = 0; c < k; c++) out->J[i] |= (uint64_t)bit(J[perm[i]], perm[c]) << c;
         }
     }
 }

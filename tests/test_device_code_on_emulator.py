@@ -1,0 +1,108 @@
+"""The product's warp-level device source (circuitsimulator_b200/csrc/bg_device.cuh, bg_philox.cuh,
+bg_warp_ops.cuh) compiled for the 32-lane CPU warp emulator (tests/emu) and checked against the
+reference's vectors and the oracle.  This is a check of the SOURCE where no GPU exists; the GPU
+parity tests proper are in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from util import load, states, epm_equal, parse_stream, GOLDEN
+from oracle.oracle import states_to_numpy
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu.emu import Emu
+    return Emu()
+
+
+def test_inner_products_vs_compiled_reference_fixture(emu):
+    d = load("ref_pairs.npz")
+    a, b = states(d["a"]), states(d["b"])
+    bad = [i for i, (s1, s2, w) in enumerate(zip(a, b, d["epm"])) if not epm_equal(emu.inner_product(s1, s2), tuple(w))]
+    assert not bad, bad[:10]
+
+
+def test_reference_inner_product_kat(emu):
+    d = load("kat_inner_product.npz")
+    for s1, s2, w in zip(states(d["a"]), states(d["b"]), d["epm"]):
+        assert epm_equal(emu.inner_product(s1, s2), tuple(w))
+
+
+def test_exponential_sum_kats(emu, oracle):
+    d = load("kat_exponential_sum.npz")
+    for s, w in list(zip(states(d["states"]), d["epm"]))[::3]:
+        plus = oracle.identity_state(s.n, s.n)
+        assert epm_equal(emu.inner_product(s, plus), (int(w[0]), int(w[1]) - 2 * s.n, int(w[2])))
+
+
+def test_measure_pauli_kats(emu, oracle):
+    d = load("kat_measure_pauli.npz")
+    for s, want, m, z, x, res in zip(states(d["states_in"]), states(d["states_out"]), d["m"], d["zeta"], d["xi"], d["result"]):
+        code, got = emu.measure_pauli(s, int(m), int(z), int(x))
+        val = {0: 0.0, 1: 1.0, 2: 2 ** -0.5}[code]
+        assert abs(val - res) < 1e-4
+        assert got.k == want.k
+        assert epm_equal(oracle.inner_product(got, want), (1, 0, 0))
+        for j in range(3):
+            pr = oracle.random_state_philox(got.n, 5, 0, j)
+            assert epm_equal(oracle.inner_product(got, pr), oracle.inner_product(want, pr))
+
+
+def test_rng_matches_oracle_restatement(emu, oracle):
+    for n in (1, 3, 16, 32, 33, 40, 64):
+        cdf = oracle.dimension_cdf(n)
+        for s in range(8):
+            a = emu.random_state(n, 2024, 3, s, cdf)
+            b = oracle.random_state_philox(n, 2024, 3, s)
+            assert a.key(full=False) == b.key(full=False)
+
+
+def _terms(cfg, L, oracle):
+    t = cfg["t"]
+    if cfg["exact"]:
+        size = (t + 1) // 2
+        return [sum(((i >> (size - 1 - j)) & 1) << (2 * j) for j in range(size)) for i in range(1 << size)]
+    return [oracle.Lbits(i, L) for i in range(1 << len(L))]
+
+
+@pytest.mark.parametrize("stream,k,ns", [("htstack_t4.txt", 0, 24), ("hs_t16_bit6.txt", 0, 3),
+                                         ("hs_t40_k9_bit0.txt", 5, 3), ("phase_estimation_q0.txt", 4, 3),
+                                         ("toffoli_q0.txt", 0, 2)])
+def test_L_chi_loop_vs_oracle(emu, oracle, stream, k, ns):
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t, exact = cfg["t"], cfg["exact"]
+    rs = np.random.RandomState(3)
+    L = [] if exact else [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+    terms = _terms(cfg, L, oracle)
+    for P in (G, H):
+        for s in range(ns):
+            th = oracle.random_state_philox(t, 7, 0, s)
+            want = oracle.sample_from_theta(th, P, exact, L)
+            got = emu.terms(th, P, 1, exact, t, terms)
+            assert got["alive"] == want["alive"]
+            if not want["alive"]:
+                continue
+            assert all(epm_equal(tuple(got["epm"][i]), tuple(want["epm"][i])) for i in range(len(terms)))
+            sh, a, r2 = t // 2 + 1, got["zw"], 2 ** -0.5
+            tot = complex(a[0] + (a[1] - a[3]) * r2, a[2] + (a[1] + a[3]) * r2) / 2 ** sh
+            assert abs(tot - want["total"]) <= 1e-12 * max(1.0, abs(want["total"]))
+            assert abs(2 ** (-got["npf"] / 2) - want["projfactor"]) < 1e-15
+
+
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(GOLDEN) if f.startswith("ref_samples_")))
+def test_L_chi_loop_vs_compiled_reference_fixture(emu, oracle, name):
+    d = load(name)
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", str(d["stream"])))
+    t, exact = cfg["t"], cfg["exact"]
+    L = [int(x) for x in d["L"]]
+    terms = _terms(dict(cfg, exact=exact), L, oracle)
+    th = states(d["theta"])
+    n = min(len(th), 4 if t > 20 else 40)
+    for l in range(n):
+        P = (G, H)[int(d["which"][l])]
+        got = emu.terms(th[l], P, 1, exact, t, terms)
+        assert got["alive"] == d["alive"][l]
+        if d["alive"][l]:
+            assert all(epm_equal(tuple(got["epm"][i]), tuple(d["epm"][l][i])) for i in range(len(terms)))

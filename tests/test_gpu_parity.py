@@ -1,0 +1,245 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(include/bgnorm.h, via circuitsimulator_b200's ctypes face) and is compared with
+  * the reference's own golden vectors (tests/golden/kat_*.npz),
+  * outputs of the compiled reference recorded in tests/golden/ref_*.npz,
+  * the CPU oracle (oracle/) on the same seeded inputs.
+Predicate for amplitudes: eps equal; if eps != 0, p equal and m equal mod 8 — the reference's own
+convention (tests/units/stabtests.c:371-376).  fp64 results: 1e-12 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from util import load, states, epm_equal, parse_stream, GOLDEN
+from oracle.oracle import states_to_numpy, state_from_numpy, Projector as OProj
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def be():
+    import circuitsimulator_b200 as bg
+    b = bg.Backend(0)
+    yield b
+    b.close()
+
+
+def to_bg(P):
+    import circuitsimulator_b200 as bg
+    return bg.Projector.make(P.nqubits, list(P.phase[:P.nstabs]), list(P.xs[:P.nstabs]), list(P.zs[:P.nstabs]))
+
+
+def exact_terms(t):
+    size = (t + 1) // 2
+    return 1 << size
+
+
+def test_library_is_cuda_only():
+    import circuitsimulator_b200 as bg
+    lib = bg.load_library()
+    assert os.path.basename(lib._name) == "libbgnorm.so"
+
+
+def test_inner_product_reference_kat(be):
+    d = load("kat_inner_product.npz")
+    got = be.inner_products(d["a"], d["b"])
+    for g, w in zip(got, d["epm"]):
+        assert epm_equal(tuple(g), tuple(w))
+
+
+def test_inner_products_vs_compiled_reference(be):
+    d = load("ref_pairs.npz")
+    got = be.inner_products(d["a"], d["b"])
+    bad = [i for i, (g, w) in enumerate(zip(got, d["epm"])) if not epm_equal(tuple(g), tuple(w))]
+    assert not bad, bad[:10]
+    assert sum(1 for w in d["epm"] if w[0] == 0) > 100       # zero detection is exercised
+
+
+def test_exponential_sum_kats_through_inner_product(be, oracle):
+    """<+^n | K,q> = 2^-n sum_x e^{i pi q(x)/4}: the reference's 274 exponential-sum vectors
+    (k = n, G = I) checked through the inner-product entry point."""
+    d = load("kat_exponential_sum.npz")
+    st = d["states"]
+    plus = states_to_numpy([oracle.identity_state(int(s["n"]), int(s["n"])) for s in st])
+    got = be.inner_products(st, plus)
+    for g, w, s in zip(got, d["epm"], st):
+        n = int(s["n"])
+        want = (int(w[0]), int(w[1]) - 2 * n, int(w[2]))
+        assert epm_equal(tuple(g), want)
+
+
+def test_measure_pauli_kats(be, oracle):
+    """Device measurePauli on the reference's 30 vectors.  The device keeps a different (equivalent)
+    basis, so states are compared as states: same k, same affine space, and identical overlaps with
+    probe states."""
+    d = load("kat_measure_pauli.npz")
+    out, res = be.measure_pauli(d["states_in"], d["m"], d["zeta"], d["xi"])
+    want_states = states(d["states_out"])
+    for i in range(len(out)):
+        assert abs(res[i] - d["result"][i]) < 1e-4
+        got = state_from_numpy(out[i])
+        want = want_states[i]
+        assert got.k == want.k
+        probes = [oracle.random_state_philox(got.n, 77, 0, j) for j in range(6)] + [want]
+        for pr in probes:
+            assert epm_equal(oracle.inner_product(got, pr), oracle.inner_product(want, pr))
+        assert epm_equal(oracle.inner_product(got, want), (1, 0, 0))      # <want|got> = 1 exactly
+
+
+def test_device_rng_matches_oracle_restatement(be, oracle):
+    for t in (1, 2, 5, 16, 32, 33, 40, 64):
+        got = be.random_states(t, 2024, 3, 10, 24)
+        for j in range(24):
+            a = state_from_numpy(got[j])
+            b = oracle.random_state_philox(t, 2024, 3, 10 + j)
+            assert a.key(full=False) == b.key(full=False), (t, j)
+
+
+def test_decomposition_terms_match_prepH_prepL(be, oracle):
+    be.set_decomposition(7, True)
+    got = be.decomposition_terms(0, 16)
+    for i in range(16):
+        a, b = state_from_numpy(got[i]), oracle.prepH(i, 7)
+        assert a.k == b.k and epm_equal(oracle.inner_product(a, b), (1, 0, 0))
+    L = [0b1011001110, 0b0110110101, 0b1110001011]
+    be.set_decomposition(10, False, L)
+    got = be.decomposition_terms(0, 8)
+    for i in range(8):
+        a, b = state_from_numpy(got[i]), oracle.prepL(i, 10, L)
+        assert a.k == b.k and epm_equal(oracle.inner_product(a, b), (1, 0, 0))
+
+
+def _fixture_names():
+    return sorted(f for f in os.listdir(GOLDEN) if f.startswith("ref_samples_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", _fixture_names())
+def test_L_chi_loop_vs_compiled_reference(be, name):
+    """theta drawn by the reference (libc rand), projected ON THE DEVICE, chi terms: per-pair
+    (eps,p,m) against the compiled reference's, per-sample value against its fp64."""
+    d = load(name)
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", str(d["stream"])))
+    t, exact = cfg["t"], cfg["exact"]
+    L = [int(x) for x in d["L"]]
+    be.set_decomposition(t, exact, L)
+    chi = d["epm"].shape[1]
+    for which, P in enumerate((G, H)):
+        sel = np.where(d["which"] == which)[0]
+        out = be.sampled_norm_from_states(to_bg(P), d["theta"][sel], project=True, want_epm=True, chi=chi)
+        for j, l in enumerate(sel):
+            if not d["alive"][l]:
+                assert out["per_sample"][j] == 0.0
+                continue
+            bad = [i for i in range(chi) if not epm_equal(tuple(out["epm"][j, i]), tuple(d["epm"][l, i]))]
+            assert not bad, (name, l, bad[:5])
+            want = d["value"][l]
+            assert abs(out["per_sample"][j] - want) <= 1e-11 * max(abs(want), 1e-300), (out["per_sample"][j], want)
+        # same thetas already projected by the reference, no device projection: same amplitudes
+        alive = [l for l in sel if d["alive"][l]]
+        if alive:
+            out2 = be.sampled_norm_from_states(to_bg(P), d["projected"][alive], project=False, want_epm=True, chi=chi)
+            for j, l in enumerate(alive):
+                assert all(epm_equal(tuple(out2["epm"][j, i]), tuple(d["epm"][l, i])) for i in range(chi))
+
+
+@pytest.mark.parametrize("stream,k,samples", [("htstack_t4.txt", 0, 256), ("hs_t16_bit6.txt", 0, 48),
+                                              ("hs_t40_k9_bit0.txt", 6, 24), ("phase_estimation_q0.txt", 5, 24)])
+def test_sampled_norm_vs_oracle_same_seed(be, oracle, stream, k, samples):
+    """bg_sampled_norm (device RNG + projection + chi loop + reduction) against the oracle running
+    the same Philox thetas through its restatement of singleProjectorSample."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t, exact = cfg["t"], cfg["exact"]
+    rs = np.random.RandomState(1)
+    L = [] if exact else [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+    be.set_decomposition(t, exact, L)
+    for P, seed in ((G, 11), (H, 12)):
+        got = be.sampled_norm(to_bg(P), samples, 1, seed, 1.0)
+        tot, per = oracle.sampled_sum_philox(P, exact, L, seed, 0, 0, 1, samples)
+        want = tot / samples
+        assert abs(got - want) <= RTOL * max(abs(want), 1e-300), (got, want)
+
+
+def test_shards_add_up(be):
+    """Strided sample shards (the reference's rank stride) sum to the single-rank result."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
+    be.set_decomposition(cfg["t"], True)
+    P = to_bg(G)
+    whole = be.sampled_norm(P, 1000, 1, 5, 1.0)
+    be.set_allreduce(False)
+    try:
+        parts = []
+        for r in range(3):
+            be.set_shard(r, 3)
+            parts.append(be.sampled_norm(P, 1000, 1, 5, 1.0))
+    finally:
+        be.set_shard(0, 1)
+        be.set_allreduce(True)
+    assert abs(sum(parts) - whole) <= 1e-13 * abs(whole)
+
+
+@pytest.mark.parametrize("stream", ["htstack_t4.txt", "toffoli_q0.txt"])
+def test_exact_norm_vs_oracle(be, oracle, stream):
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t = cfg["t"]
+    be.set_decomposition(t, True)
+    for P in (G, H):
+        got = be.exact_norm(to_bg(P), 1.0)
+        want = oracle.exact_projector(P, True, [], 1.0)
+        assert abs(got - want) <= 1e-11 * max(abs(want), 1e-300), (got, want)
+
+
+def test_exact_norm_L_decomposition_vs_oracle(be, oracle):
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "phase_estimation_q0.txt"))
+    t = cfg["t"]
+    rs = np.random.RandomState(9)
+    L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(5)]
+    be.set_decomposition(t, False, L)
+    got = be.exact_norm(to_bg(G), 1.0)
+    want = oracle.exact_projector(G, False, L, 1.0)
+    assert abs(got - want) <= 1e-11 * max(abs(want), 1e-300)
+
+
+def test_backend_executable_end_to_end():
+    """The unmodified front end's instruction streams through the drop-in executable
+    (stdin protocol of libcirc/probability.c:74-216).  Exact-norm path: deterministic."""
+    import json
+    import circuitsimulator_b200 as bg
+    meta = json.load(open(os.path.join(GOLDEN, "streams", "meta.json")))
+    # HTstack: without -forceSample the back end switches to the exact norm (probability.c:162-167)
+    txt = open(os.path.join(GOLDEN, "streams", "htstack_t4.txt")).read().split()
+    txt[12] = "0"                                           # forceSample off
+    num, den, _ = bg.run_backend("\n".join(txt) + "\n", env={"BG_SEED": 1})
+    assert abs(num / den - meta["htstack_t4"]["expect_probability"]) < 1e-7
+    num, den, _ = bg.run_backend(open(os.path.join(GOLDEN, "streams", "toffoli_111.txt")).read(), env={"BG_SEED": 1})
+    assert abs(num / den - 1.0) < 1e-9                      # circuits/toffoli.circ:14-19 -> 111 with certainty
+    # sampled path on the same circuit: estimator within its statistical error
+    num, den, _ = bg.run_backend(open(os.path.join(GOLDEN, "streams", "htstack_t4.txt")).read(), env={"BG_SEED": 3})
+    assert abs(num / den - 0.97855339) < 0.15
+
+
+def test_full_size_config4_properties(be):
+    """BASELINE config 4 at full size (t=40, chi=512, L=2^16): determinism under the same seed,
+    independence from the work partition, and additivity of sample shards."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t40_k9_bit0.txt"))
+    t = cfg["t"]
+    rs = np.random.RandomState(4)
+    L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(9)]
+    be.set_decomposition(t, False, L)
+    P = to_bg(G)
+    a = be.sampled_norm(P, 65536, 1, 42, 1.0)
+    st = be.stats()
+    assert st["pairs"] == 65536 * 512
+    b = be.sampled_norm(P, 65536, 1, 42, 1.0)
+    assert a == b
+    be.set_allreduce(False)
+    try:
+        parts = []
+        for r in range(2):
+            be.set_shard(r, 2)
+            parts.append(be.sampled_norm(P, 65536, 1, 42, 1.0))
+    finally:
+        be.set_shard(0, 1)
+        be.set_allreduce(True)
+    assert abs(sum(parts) - a) <= 1e-13 * abs(a)
+    assert a > 0

@@ -1,0 +1,122 @@
+"""Host-side logic and the C-ABI surface, no GPU needed: the shared library loads and exports every
+symbol include/bgnorm.h declares; without a device the product fails loudly (no CPU fallback);
+the drop-in executable parses the reference's token protocol; the sample sharding used for N GPUs
+is exercised with a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import parse_stream, GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _built():
+    import circuitsimulator_b200 as bg
+    if not os.path.exists(bg.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return bg
+
+
+def test_header_symbols_exported():
+    bg = _built()
+    lib = bg.load_library()
+    header = open(os.path.join(ROOT, "include", "bgnorm.h")).read()
+    declared = sorted(set(re.findall(r"\b(bg_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(bg.exported_symbols()) == declared
+
+
+def test_struct_layouts_match():
+    bg = _built()
+    from oracle.oracle import State, Projector
+    assert bg.STATE_DTYPE.itemsize == ctypes.sizeof(State) == 16 + 24 + 3 * 64 * 8
+    assert ctypes.sizeof(bg.Projector) == ctypes.sizeof(Projector)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    bg = _built()
+    with pytest.raises(bg.BGError) as e:
+        bg.Backend(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_touch_oracle():
+    """The product package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "circuitsimulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "packed_oracle" not in txt and "libcircref" not in txt, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+
+
+def test_backend_protocol_errors_are_unparsable_lines():
+    """Errors are printed strings, never floats, so libcirc/probability.py:302-312 raises."""
+    bg = _built()
+    p = subprocess.run([bg.BACKEND_PATH, "stdin"], input=b"0 0 0 10 1 4 0 1 1e-5 0 0 0 1 2 4 0\n",
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    last = p.stdout.decode().splitlines()[-1]
+    with pytest.raises(ValueError):
+        float(last)
+    p = subprocess.run([bg.BACKEND_PATH, "/nonexistent/file"], stdout=subprocess.PIPE)
+    assert "Error reading file" in p.stdout.decode()
+
+
+def test_backend_clifford_closed_form_needs_no_gpu():
+    """t = 0 (Clifford circuit): the closed form of innerprod.c:52-62 is evaluated on the host."""
+    bg = _built()
+    # two projectors on 0 qubits: G = {+I, -I}, H = {+I}
+    txt = "0 0 0 100 1 0 0 1 1e-5 0 0 0 0\n2 0 0 2\n1 0 0\n"
+    num, den, _ = bg.run_backend(txt)
+    assert abs(num - (1 + 1 - 1) / 3.0) < 1e-15 and abs(den - 1.0) < 1e-15
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle.oracle import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = Oracle()
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "htstack_t4.txt"))
+    samples = 37
+    count = samples // world + (1 if rank < samples % world else 0)        # shard_count() of bgnorm.cu
+    part, _ = o.sampled_sum_philox(G, True, [], 9, 0, rank, world, count)   # l = rank + world*j
+    t = torch.tensor([part, float(count)], dtype=torch.float64)
+    dist.all_reduce(t)
+    if rank == 0:
+        q.put((float(t[0]), float(t[1])))
+    dist.destroy_process_group()
+
+
+def test_strided_sharding_world2_gloo(oracle):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    total, count = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "htstack_t4.txt"))
+    whole, _ = oracle.sampled_sum_philox(G, True, [], 9, 0, 0, 1, 37)
+    assert count == 37
+    assert abs(total - whole) <= 1e-13 * abs(whole)
