@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from util import load, states, epm_equal, parse_stream, GOLDEN
+from util import load, states, epm_equal, parse_stream, exact_sample_value, GOLDEN
 from oracle.oracle import states_to_numpy, state_from_numpy, Projector as OProj
 
 pytestmark = pytest.mark.gpu
@@ -133,8 +133,13 @@ def test_L_chi_loop_vs_compiled_reference(be, name):
                 continue
             bad = [i for i in range(chi) if not epm_equal(tuple(out["epm"][j, i]), tuple(d["epm"][l, i]))]
             assert not bad, (name, l, bad[:5])
-            want = d["value"][l]
-            assert abs(out["per_sample"][j] - want) <= 1e-11 * max(abs(want), 1e-300), (out["per_sample"][j], want)
+            # the device value against the EXACT value of the reference's own amplitudes (1e-12
+            # relative), and against the reference's fp64, whose sequential cos/sin/pow summation
+            # (innerprod.c:127-142) carries an absolute error ~1e-16 * (sum |terms|)^2
+            exact, scale = exact_sample_value(d["epm"][l], t, d["projfactor"][l])
+            got = out["per_sample"][j]
+            assert abs(got - exact) <= RTOL * abs(exact), (got, exact)
+            assert abs(got - d["value"][l]) <= RTOL * abs(exact) + 1e-13 * scale, (got, d["value"][l])
         # same thetas already projected by the reference, no device projection: same amplitudes
         alive = [l for l in sel if d["alive"][l]]
         if alive:
@@ -229,7 +234,7 @@ def test_full_size_config4_properties(be):
     P = to_bg(G)
     a = be.sampled_norm(P, 65536, 1, 42, 1.0)
     st = be.stats()
-    assert st["pairs"] == 65536 * 512
+    assert 0.9 * 65536 * 512 <= st["pairs"] <= 65536 * 512        # annihilated samples evaluate no pairs
     b = be.sampled_norm(P, 65536, 1, 42, 1.0)
     assert a == b
     be.set_allreduce(False)

@@ -78,3 +78,36 @@ def parse_stream(path):
             zs.append(z)
         projs.append(Projector.make(nq, ph, xs, zs))
     return cfg, projs[0], projs[1]
+
+
+def exact_sample_value(epm, t, projfactor):
+    """2^t |projfactor * sum_i eps_i 2^{p_i/2} w^{m_i}|^2 evaluated EXACTLY in Z[sqrt2] with Python
+    integers (then rounded once), from per-pair (eps, p, m) triples.  Used to judge fp64 results
+    whose own summation error is amplified by cancellation."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 80
+    sh = t // 2 + 1
+    a = [0, 0, 0, 0]
+
+    def add(e, mag):
+        e %= 8
+        a[e & 3] += -mag if e & 4 else mag
+
+    for eps, p, m in epm:
+        eps, p, m = int(eps), int(p), int(m)
+        if not eps:
+            continue
+        f = p // 2                      # floor
+        mag = 1 << (sh + f)
+        if p % 2 == 0:
+            add(m, mag)
+        else:
+            add(m + 1, mag)
+            add(m - 1, mag)
+    X = sum(v * v for v in a)
+    Y = a[0] * a[1] + a[1] * a[2] + a[2] * a[3] - a[0] * a[3]
+    npf = int(round(-2 * np.log2(projfactor))) if projfactor > 0 else 0
+    val = (Decimal(X) + Decimal(2).sqrt() * Decimal(Y)) * (Decimal(2) ** (t - npf - 2 * sh))
+    mags = sum(2.0 ** (int(p_) / 2) for e_, p_, m_ in epm if int(e_))      # sum_i |term_i| (before cancellation)
+    scale = mags * mags * 2.0 ** (t - npf)
+    return float(val), scale
