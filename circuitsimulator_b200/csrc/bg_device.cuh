@@ -33,11 +33,13 @@
 #if defined(__CUDACC__)
 #define BG_DEV __device__ __forceinline__
 #define BG_HD __host__ __device__ __forceinline__
+#define BG_HDM __host__ __device__ __forceinline__
 BG_DEV int bg_lane() { return (int)(threadIdx.x & 31u); }
 #else
 #include "cpu_warp.h"   // tests/emu: __shfl_sync, __ballot_sync, __reduce_xor_sync, __popc, __ffs, ... bg_lane()
 #define BG_DEV static inline
 #define BG_HD static inline
+#define BG_HDM inline
 #endif
 
 #define BG_FULL 0xffffffffu

@@ -1,0 +1,230 @@
+// bg_tpp.cuh — the L x chi hot loop, one THREAD per inner product.
+//
+// A warp takes one projected theta (its ambient quadratic form, see bg_device.cuh) and 32
+// decomposition terms at a time: lane j evaluates <phi_{i0+j} | theta>.  Every quantity that is
+// warp-uniform in the warp-per-pair formulation (D, the active set, the pivot rows, ...) is here a
+// per-thread register, so no lane-op is spent on replicated work; the only per-thread array is the
+// working copy of J (t rows of one word), kept in shared memory in a [row][thread] layout — bank =
+// thread, so the data-dependent row index never causes a bank conflict.
+//
+// Why: ncu on the warp-per-pair kernel (profiles/r1_v1_warp_per_pair_ncu_summary.json) shows the
+// integer ALU pipe 95 % busy at 1266 warp-instructions per inner product — a t = 40 term has only
+// ~20 live rows for 64 row slots and every uniform mask update is executed by all 32 lanes.  The
+// same algebra per thread needs ~2000 thread-instructions per pair, i.e. ~60 warp-instructions.
+//
+// Same mathematics as bg_device.cuh (pivot / basis_change / expsum), same reference anchors:
+// shrink (stabilizer.c:500-585), updateDJ/updateQD (:129-177), exponentialSumExact (:300-481),
+// innerProductExact (:589-659), prepH/prepL (stateprep.c:36-120).
+#pragma once
+#include "bg_device.cuh"
+
+namespace bg {
+
+// per-thread view of its working rows: row r lives at base[r * stride]
+template <typename W> struct Rows {
+    W* base;
+    int stride;
+    BG_HDM W get(int r) const { return base[(size_t)r * stride]; }
+    BG_HDM void put(int r, W v) const { base[(size_t)r * stride] = v; }
+    BG_HDM void xr(int r, W v) const { base[(size_t)r * stride] ^= v; }
+};
+
+template <typename W> struct TF {      // per-thread quadratic form scalars (J is in Rows)
+    W D1, D2, A;
+    uint32_t Q;
+};
+
+BG_HD int tlowest(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+BG_HD int tlowest(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+BG_HD int tpopc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+BG_HD int tpopc(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+template <typename W> BG_HD W tbit(int i) { return (W)1 << i; }
+template <typename W> BG_HD W tfill(uint32_t b) { return (W)0 - (W)(b & 1u); }
+template <typename W> BG_HD uint32_t tget(W x, int i) { return (uint32_t)(x >> i) & 1u; }
+template <typename W> BG_HD W tlowmask(int n) { return n >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << n) - 1); }
+
+// x_i = x'_i + sum_{a in Sp} x'_a.   (bg_device.cuh: basis_change)   Returns the old row i.
+template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, W Sp) {
+    const W bi = tbit<W>(i);
+    const W Ji = J.get(i);
+    for (W r = Sp; r; r &= r - 1) J.xr(tlowest(r), Ji);                 // row a += row i
+    // column a += column i: rows r whose (updated) entry (r,i) is set.  By symmetry that column is
+    // row i, plus J_ii on the rows of Sp.
+    const W col = (Ji ^ ((Ji & bi) ? Sp : (W)0)) & f.A;
+    for (W r = col; r; r &= r - 1) J.xr(tlowest(r), Sp);
+    const W d1i = tfill<W>(tget(f.D1, i)), d2i = tfill<W>(tget(f.D2, i));
+    f.D2 ^= Sp & (d2i ^ (d1i & f.D1) ^ Ji);
+    f.D1 ^= Sp & d1i;
+    return Ji;
+}
+
+// impose sum_{a in S} x_a = beta, eliminating x_i, i = lowest(S)    (bg_device.cuh: pivot)
+template <typename W> BG_HD void t_pivot(const Rows<W>& J, TF<W>& f, W S, uint32_t beta) {
+    const int i = tlowest(S);
+    const W bi = tbit<W>(i), Sp = S ^ bi;
+    const uint32_t d1 = tget(f.D1, i), d2 = tget(f.D2, i);
+    const W Ji = t_basis_change<W>(J, f, i, Sp);
+    if (beta) {
+        f.Q = (f.Q + 2u * d1 + 4u * d2) & 7u;
+        f.D2 ^= Ji ^ (Sp & tfill<W>(d1));
+    }
+    f.A &= ~bi;
+}
+
+// sum over F_2^A of e^{i pi q/4}    (bg_device.cuh: expsum)
+template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, int& p, int& m) {
+    const W A = f.A;
+    const W S = f.D1 & A;
+    const bool has_s = S != 0;
+    W E = A, Js = 0;
+    uint32_t Ds = 0;
+    if (has_s) {
+        const int s = tlowest(S);
+        const W bs = tbit<W>(s), Sp = S ^ bs;
+        Ds = 2u + 4u * tget(f.D2, s);
+        if (Sp) t_basis_change<W>(J, f, s, Sp);
+        E = A & ~bs;
+        Js = J.get(s) & E;
+    }
+    W D2 = f.D2;
+    uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
+    while (E) {
+        const int a = tlowest(E);
+        const W ba = tbit<W>(a);
+        const W Ja = J.get(a) & E & ~ba;
+        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
+        if (Ja == 0) {
+            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
+            E ^= ba;
+            if (z0 && (z1 || !has_s)) break;
+            continue;
+        }
+        const int b = tlowest(Ja);
+        const W bb = tbit<W>(b);
+        const W Jb = J.get(b) & E & ~bb;
+        const W rest = E & ~(ba | bb);
+        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
+        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
+        const W Jar = Ja & rest, Jbr = Jb & rest;
+        const W both = Jar & Jbr, onlyA = Jar ^ both, onlyB = Jbr ^ both, JJ = Jar ^ Jbr;
+        for (W r = onlyA; r; r &= r - 1) J.xr(tlowest(r), Jbr);         // J_c[a] only
+        for (W r = onlyB; r; r &= r - 1) J.xr(tlowest(r), Jar);         // J_c[b] only
+        for (W r = both; r; r &= r - 1) J.xr(tlowest(r), JJ);           // both
+        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ both;
+        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
+        E = rest;
+    }
+    p = 2 * (int)cnt;
+    const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
+    if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; return; }
+    const uint32_t m1 = (f.Q + Ds + 4u * neg1) & 7u;
+    if (z0 && z1) { eps = 0; m = 0; p = 0; return; }
+    eps = 1;
+    if (z0) { m = (int)m1; return; }
+    if (z1) { m = (int)m0; return; }
+    const uint32_t diff = (m1 - m0) & 7u;
+    p += 1;
+    m = (int)((m0 + (diff == 2u ? 1u : 7u)) & 7u);
+}
+
+// What a warp shares about its theta: the ambient form and at most TPP_MAXC parity checks.
+#define TPP_MAXC 6
+template <typename W> struct TShared {
+    const W* J;          // t ambient rows (shared memory, read-only)
+    W D1, D2;
+    uint32_t Q;
+    int k1, t;
+    int ncons;           // parity checks (t - k1), <= TPP_MAXC
+    W cw[TPP_MAXC];
+    uint32_t cbeta;      // bit j = right-hand side of check j
+};
+
+// membership checks of K_theta, restricted to this term's active set.  Earlier pivots are
+// substituted lazily (check j is rewritten with the pivots of checks < j).  `mrg` != 0: variables
+// 2j in mrg were merged into 2j+1 beforehand (prepH), so bit 2j of a check moves to bit 2j+1.
+template <typename W>
+BG_HD bool t_constraints(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, W mrg) {
+    W hs[TPP_MAXC];
+    uint32_t hb = 0;
+#pragma unroll
+    for (int j = 0; j < TPP_MAXC; j++) {
+        if (j >= sh.ncons) break;
+        W w = sh.cw[j];
+        w ^= (w & mrg) << 1;
+        uint32_t beta = (sh.cbeta >> j) & 1u;
+#pragma unroll
+        for (int q = 0; q < TPP_MAXC; q++) {            // substitute the pivots of checks q < j, in order
+            if (q >= j) break;
+            if (w & (hs[q] & (~hs[q] + 1))) { w ^= hs[q]; beta ^= (hb >> q) & 1u; }
+        }
+        w &= f.A;
+        hs[j] = w;                                       // 0 when the check is already implied
+        hb |= beta << j;
+        if (w == 0) { if (beta) return false; continue; }
+        t_pivot<W>(J, f, w, beta);
+    }
+    return true;
+}
+
+// <phi|theta> for a |L> term (prepL): |+> on supp(xt), |0> elsewhere.
+template <typename W>
+BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
+    const int t = sh.t;
+    for (int q = 0; q < t; q++) J.put(q, sh.J[q]);
+    TF<W> f;
+    f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
+    f.A = xt & tlowmask<W>(t);
+    const int k2 = tpopc(f.A);
+    if (!t_constraints<W>(J, f, sh, (W)0)) { eps = 0; p = 0; m = 0; return; }
+    t_expsum<W>(J, f, eps, p, m);
+    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
+}
+
+// <phi|theta> for a |H^t> term (prepH); e1 as in bg_device.cuh: term_H.
+template <typename W>
+BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int& p, int& m) {
+    const int t = sh.t;
+    const W maskt = tlowmask<W>(t);
+    const W pairs = (W)0x5555555555555555ull & (maskt >> 1);
+    const W mrg = e1 & pairs, cz = ~e1 & pairs;
+    const W last = (t & 1) ? (e1 & tbit<W>(t - 1)) : (W)0;
+    const W cz2 = cz | (cz << 1);
+    for (int q = 0; q < t; q++) J.put(q, sh.J[q] ^ (((cz2 >> q) & 1) ? tbit<W>(q ^ 1) : (W)0));     // q1 - q2
+    TF<W> f;
+    f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
+    f.A = maskt & ~last;
+    for (W r = mrg; r; r &= r - 1) {                    // x_{2j} = x_{2j+1}
+        const int i = tlowest(r);
+        t_pivot<W>(J, f, tbit<W>(i) | tbit<W>(i + 1), 0u);
+    }
+    const int k2 = t - tpopc(mrg) - tpopc(last);
+    if (!t_constraints<W>(J, f, sh, mrg)) { eps = 0; p = 0; m = 0; return; }
+    t_expsum<W>(J, f, eps, p, m);
+    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
+}
+
+}  // namespace bg

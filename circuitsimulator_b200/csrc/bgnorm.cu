@@ -30,12 +30,17 @@
 #include "bg_device.cuh"
 #include "bg_philox.cuh"
 #include "bg_warp_ops.cuh"
+#include "bg_tpp.cuh"
 
 using namespace bg;
 
 // ------------------------------------------------------------------------------------------
 // device-side records
 // ------------------------------------------------------------------------------------------
+// alive: 0 = annihilated by the projector; ROUTE_TPP = evaluated by k_pairs_tpp (one thread per
+// inner product); ROUTE_WARP = evaluated by k_pairs (one warp per inner product: any number of
+// parity checks).
+enum { ROUTE_DEAD = 0, ROUTE_TPP = 1, ROUTE_WARP = 2 };
 struct SampleRec {          // one projected theta in ambient form (see bg_device.cuh: ambient())
     int32_t alive, k1, npf, Q;
     uint64_t D1, D2, Cpend, Cbeta;
@@ -60,6 +65,8 @@ struct PrepArgs {
     const uint64_t* terms; int exact;
     // optional dump of the native state before projection (active-mask layout)
     bg_state* raw_out; uint64_t* raw_A;
+    int force_warp;                     // route every sample to the warp-per-pair kernel
+    unsigned long long* n_warp_routed;  // device counter
 };
 
 struct PairArgs {
@@ -77,6 +84,7 @@ struct PairArgs {
     int tri;                // exact-norm mode: sample i meets terms j >= first_index(i)
     uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
+    const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
 };
 
 // ------------------------------------------------------------------------------------------
@@ -132,7 +140,9 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
         Ambient<NS> am;
         make_ambient<NS>(st, am);
         if (lane == 0) {
-            r->alive = 1; r->k1 = am.k1; r->npf = npf; r->Q = (int32_t)am.f.Q;
+            const int route = (a.force_warp || popcw(am.Cpend) > TPP_MAXC) ? ROUTE_WARP : ROUTE_TPP;
+            if (route == ROUTE_WARP) atomicAdd(a.n_warp_routed, 1ull);
+            r->alive = route; r->k1 = am.k1; r->npf = npf; r->Q = (int32_t)am.f.Q;
             r->D1 = (uint64_t)am.f.D1; r->D2 = (uint64_t)am.f.D2;
             r->Cpend = (uint64_t)am.Cpend; r->Cbeta = (uint64_t)am.Cbeta;
         }
@@ -183,6 +193,7 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
     uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ __align__(8) uint64_t s_mbar;
     const int lane = bg_lane();
+    if (*a.n_warp_routed == 0ull) return;       // every sample went to k_pairs_tpp
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
 
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
         const int idx = (int)(item / (unsigned)a.chunks_per_sample);
         const int c = (int)(item % (unsigned)a.chunks_per_sample);
         const SampleRec* r = &a.recs[idx];
-        if (!r->alive) continue;
+        if (r->alive != ROUTE_WARP) continue;
         int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
         long long diag_index = -1;
         if (a.tri) {                                // exactProjectorWork: pairs (i, j >= i)
@@ -235,6 +246,108 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
             for (int j = 0; j < 4; j++) {
                 if (z.a[j]) atomicAdd((unsigned long long*)&a.zw[(size_t)idx * 4 + j], (unsigned long long)z.a[j]);
                 if (a.tri && z2.a[j]) atomicAdd((unsigned long long*)&a.zw2[(size_t)idx * 4 + j], (unsigned long long)z2.a[j]);
+            }
+        }
+    }
+    if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pairs_tpp: one thread per inner product (bg_tpp.cuh).  A warp = one theta x 32 terms.
+// dynamic smem: [staged terms][ambient J: warps x t words][working rows: t x blockDim words]
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
+    uint32_t lo = __shfl_down_sync(BG_FULL, (uint32_t)(unsigned long long)v, d);
+    uint32_t hi = __shfl_down_sync(BG_FULL, (uint32_t)((unsigned long long)v >> 32), d);
+    return (long long)(((unsigned long long)hi << 32) | lo);
+}
+
+template <typename W, bool EXACT, bool TRI>
+__global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int lane = bg_lane(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int t = a.t;
+    uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
+    W* s_amb = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + warp * t;
+    W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * t + threadIdx.x;
+    if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
+    const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
+    Rows<W> rows; rows.base = s_rows; rows.stride = blockDim.x;
+
+    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)a.chunks_per_sample;
+    const int sh_ = t / 2 + 1;
+    unsigned long long my_pairs = 0;
+    while (true) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ull);
+        item = __shfl_sync(BG_FULL, item, 0);
+        if (item >= n_items) break;
+        const int idx = (int)(item / (unsigned)a.chunks_per_sample);
+        const int c = (int)(item % (unsigned)a.chunks_per_sample);
+        const SampleRec* r = &a.recs[idx];
+        if (r->alive != ROUTE_TPP) continue;
+        int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
+        long long diag_index = -1;
+        if (TRI) {
+            diag_index = (long long)(a.first + (uint64_t)idx * a.stride);
+            if ((long long)i0 < diag_index) i0 = (int)diag_index;
+        }
+        if (i0 >= i1) continue;
+        __syncwarp();
+        for (int q = lane; q < t; q += 32) s_amb[q] = (W)r->J[q];
+        TShared<W> sh;
+        sh.J = s_amb; sh.D1 = (W)r->D1; sh.D2 = (W)r->D2; sh.Q = (uint32_t)r->Q; sh.k1 = r->k1; sh.t = t;
+        sh.ncons = 0; sh.cbeta = 0;
+        {
+            const uint64_t cbeta = r->Cbeta;
+#pragma unroll
+            for (int j = 0; j < TPP_MAXC; j++) sh.cw[j] = 0;
+            uint64_t pend = r->Cpend;
+#pragma unroll
+            for (int j = 0; j < TPP_MAXC; j++) {
+                if (pend) {
+                    const int b = __ffsll((long long)pend) - 1;
+                    pend &= pend - 1;
+                    sh.cw[j] = (W)r->Cw[b];
+                    sh.cbeta |= (uint32_t)((cbeta >> b) & 1ull) << j;
+                    sh.ncons = j + 1;
+                }
+            }
+        }
+        __syncwarp();
+        Zw z, z2;
+        z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+        z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
+        for (int g = i0; g < i1; g += 32) {
+            const int i = g + lane;
+            if (i < i1) {
+                const W term = (W)terms[i];
+                int e, p, m;
+                if (EXACT) t_term_H<W>(rows, sh, term, e, p, m);
+                else t_term_L<W>(rows, sh, term, e, p, m);
+                if (TRI && (long long)i != diag_index) zw_add(z2, e, p, m, sh_);
+                else zw_add(z, e, p, m, sh_);
+                if (a.epm) {
+                    int32_t* o = a.epm + ((size_t)idx * a.nterms + i) * 3;
+                    o[0] = e; o[1] = p; o[2] = m & 7;
+                }
+            }
+        }
+        my_pairs += (unsigned long long)(i1 - i0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                z.a[j] += shfl_down_ll(z.a[j], d);
+                if (TRI) z2.a[j] += shfl_down_ll(z2.a[j], d);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (z.a[j]) atomicAdd((unsigned long long*)&a.zw[(size_t)idx * 4 + j], (unsigned long long)z.a[j]);
+                if (TRI && z2.a[j]) atomicAdd((unsigned long long*)&a.zw2[(size_t)idx * 4 + j], (unsigned long long)z2.a[j]);
             }
         }
     }
@@ -367,6 +480,7 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
+    int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
     double* d_red = nullptr;                    // [8] reduction outputs
@@ -434,6 +548,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
+    if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
     *out = ctx;
     return 0;
@@ -633,8 +748,11 @@ template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepA
     ctx->stats.launches++;
     return 0;
 }
-static int launch_prepare(bg_ctx* ctx, int src, const PrepArgs& a) {
+static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    a.force_warp = ctx->force_warp;
+    a.n_warp_routed = ctx->d_counters + 2;
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
 
@@ -647,7 +765,22 @@ template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const Pair
     return 0;
 }
 
-// Fill in chunking / staging and launch k_pairs.  zw (and zw2) must be zeroed already.
+template <typename W, bool EXACT, bool TRI> static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pairs_tpp<W, EXACT, TRI><<<blocks, 32 * WARPS_PER_BLOCK, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
+template <typename W> static int launch_tpp_w(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
+    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false>(ctx, a, blocks, smem);
+    return a.tri ? launch_tpp_inst<W, false, true>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false>(ctx, a, blocks, smem);
+}
+
+// Fill in chunking / staging and launch the pair kernels: k_pairs_tpp for the samples routed to it,
+// then k_pairs (returns at once when nothing was routed to it).  zw (and zw2) must be zeroed and
+// launch_prepare must have run on the same stream (it resets the counters).
 static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     if (a.n_samples <= 0) return 0;
     const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
@@ -655,20 +788,29 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     int cps = 1;
     if (a.n_samples < want_items) cps = (want_items + a.n_samples - 1) / a.n_samples;
     int chunk = (a.nterms + cps - 1) / cps;
-    if (chunk < 16) chunk = 16;
-    if (chunk > a.nterms) chunk = a.nterms;
+    chunk = (chunk + 31) & ~31;                                // whole groups of 32 terms
+    if (chunk < 32) chunk = 32;
     cps = (a.nterms + chunk - 1) / chunk;
     a.chunk = chunk; a.chunks_per_sample = cps;
     const size_t padded = ((size_t)a.nterms + 1) & ~(size_t)1;
-    a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;
-    const size_t smem = (size_t)a.smem_terms * 8;
     const unsigned long long items = (unsigned long long)a.n_samples * cps;
     long long blocks = (long long)ctx->sm_count * ctx->ctas_per_sm;   // persistent CTAs, a multiple of the SM count
     const long long need = (long long)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    a.counter = ctx->d_counters; a.pair_count = ctx->d_counters + 1;
+    a.pair_count = ctx->d_counters + 1;
+    a.n_warp_routed = ctx->d_counters + 2;
+    if (!ctx->force_warp) {
+        a.counter = ctx->d_counters;
+        a.smem_terms = padded <= 2048 ? (int)padded : 0;
+        const size_t wb = a.t <= 32 ? 4 : 8;
+        const size_t smem = (size_t)a.smem_terms * 8 + (size_t)WARPS_PER_BLOCK * a.t * wb + (size_t)a.t * 32 * WARPS_PER_BLOCK * wb;
+        if (a.t <= 32) { if (launch_tpp_w<uint32_t>(ctx, a, (int)blocks, smem)) return 1; }
+        else { if (launch_tpp_w<uint64_t>(ctx, a, (int)blocks, smem)) return 1; }
+    }
+    a.counter = ctx->d_counters + 3;
+    a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;
+    const size_t smem = (size_t)a.smem_terms * 8;
     if (a.t <= 32) return ctx->exact ? launch_pairs_ns<1, true>(ctx, a, (int)blocks, smem) : launch_pairs_ns<1, false>(ctx, a, (int)blocks, smem);
     return ctx->exact ? launch_pairs_ns<2, true>(ctx, a, (int)blocks, smem) : launch_pairs_ns<2, false>(ctx, a, (int)blocks, smem);
 }

@@ -43,6 +43,8 @@ class Emu:
         lib.emu_terms.argtypes = [_P(State), _P(Projector), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_uint64),
                                   _P(C.c_int32), _P(C.c_int), _P(C.c_int), _P(C.c_longlong)]
         lib.emu_terms.restype = C.c_int
+        lib.emu_terms_tpp.argtypes = lib.emu_terms.argtypes
+        lib.emu_terms_tpp.restype = C.c_int
         lib.emu_measure_pauli.argtypes = [_P(State), _P(C.c_uint64), C.c_int, C.c_uint64, C.c_uint64]
         lib.emu_measure_pauli.restype = C.c_int
         lib.emu_random_state.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(State),
@@ -54,12 +56,14 @@ class Emu:
         self.lib.emu_inner_product(C.byref(a), C.byref(b), out)
         return tuple(out)
 
-    def terms(self, theta, P, project, exact, t, terms):
+    def terms(self, theta, P, project, exact, t, terms, tpp=False):
+        """tpp=True: the chi loop through the thread-per-pair code (alive = -1: too many parity checks)."""
         n = len(terms)
         epm = np.zeros((n, 3), dtype=np.int32)
         npf, k = C.c_int(), C.c_int()
         zw = (C.c_longlong * 4)()
-        alive = self.lib.emu_terms(C.byref(theta), C.byref(P), int(project), int(bool(exact)), t, n,
+        fn = self.lib.emu_terms_tpp if tpp else self.lib.emu_terms
+        alive = fn(C.byref(theta), C.byref(P), int(project), int(bool(exact)), t, n,
                                    u64_array(terms), epm.ctypes.data_as(_P(C.c_int32)), C.byref(npf),
                                    C.byref(k), zw)
         return dict(alive=alive, epm=epm, npf=npf.value, k=k.value, zw=list(zw))

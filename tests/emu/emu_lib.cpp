@@ -3,6 +3,7 @@
 #include "cpu_warp.h"
 #include "bg_device.cuh"
 #include "bg_warp_ops.cuh"
+#include "bg_tpp.cuh"
 #include <string.h>
 
 namespace emu {
@@ -44,6 +45,52 @@ void run(const std::function<void()>& body) {
 
 using namespace bg;
 
+// Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
+// ambient form is produced by the warp-level code under emulation, each term is then a plain call.
+template <int NS>
+static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, int exact, int t, int nterms,
+                     const uint64_t* terms, int32_t* epm, int* npf_out, int* k_out, long long* zw_out) {
+    typedef typename WordOf<NS>::T W;
+    int alive = 1, npf = 0, k1 = 0;
+    W Jrows[64], Cwrows[64]; W D1 = 0, D2 = 0, Cpend = 0, Cbeta = 0; uint32_t Q = 0;
+    emu::run([&]() {
+        Native<NS> st; Ambient<NS> am;
+        native_load<NS>(st, theta);
+        int n = 0; bool ok = true;
+        if (project) ok = project_native<NS>(st, P, n);
+        if (ok) make_ambient<NS>(st, am);
+        const int lane = bg_lane();
+        if (lane == 0) { alive = ok; npf = n; }
+        if (ok) {
+            for (int s = 0; s < NS; s++) { Jrows[lane + 32 * s] = am.f.J[s]; Cwrows[lane + 32 * s] = am.Cw[s]; }
+            if (lane == 0) { D1 = am.f.D1; D2 = am.f.D2; Q = am.f.Q; Cpend = am.Cpend; Cbeta = am.Cbeta; k1 = am.k1; }
+        }
+    });
+    *npf_out = npf; *k_out = k1;
+    Zw z; z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+    if (alive) {
+        TShared<W> sh;
+        sh.J = Jrows; sh.D1 = D1; sh.D2 = D2; sh.Q = Q; sh.k1 = k1; sh.t = t; sh.ncons = 0; sh.cbeta = 0;
+        for (W r = Cpend; r; r &= r - 1) {
+            int b = tlowest(r);
+            if (sh.ncons >= TPP_MAXC) return -1;           // routed to the warp-per-pair kernel on the device
+            sh.cw[sh.ncons] = Cwrows[b];
+            sh.cbeta |= (uint32_t)((Cbeta >> b) & 1) << sh.ncons;
+            sh.ncons++;
+        }
+        W work[64];
+        Rows<W> rows; rows.base = work; rows.stride = 1;
+        for (int i = 0; i < nterms; i++) {
+            int e, p, m;
+            if (exact) t_term_H<W>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W>(rows, sh, (W)terms[i], e, p, m);
+            zw_add(z, e, p, m, t / 2 + 1);
+            if (epm) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m; }
+        }
+    }
+    if (zw_out) for (int j = 0; j < 4; j++) zw_out[j] = z.a[j];
+    return alive;
+}
+
 extern "C" {
 
 // <b|a> through the generic path
@@ -66,6 +113,12 @@ int emu_terms(const bg_state* theta, const bg_projector* P, int project, int exa
         else warp_sample_terms<2>(theta, P, project, exact, t, nterms, terms, epm, &alive, npf_out, k_out, zw_out);
     });
     return alive;
+}
+
+int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int exact, int t, int nterms,
+                  const uint64_t* terms, int32_t* epm, int* npf_out, int* k_out, long long* zw_out) {
+    if (t <= 32) return terms_tpp<1>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
+    return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
 }
 
 int emu_measure_pauli(bg_state* st, uint64_t* A, int m, uint64_t zeta, uint64_t xi) {
