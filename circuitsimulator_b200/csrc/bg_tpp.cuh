@@ -67,15 +67,61 @@ template <typename W> BG_HD W tfill(uint32_t b) { return (W)0 - (W)(b & 1u); }
 template <typename W> BG_HD uint32_t tget(W x, int i) { return (uint32_t)(x >> i) & 1u; }
 template <typename W> BG_HD W tlowmask(int n) { return n >= (int)(8 * sizeof(W)) ? ~(W)0 : (((W)1 << n) - 1); }
 
+// position of the highest set bit of a non-zero word: one FLO on the device
+BG_HD int thighest(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+BG_HD int thighest(uint64_t x) {
+    const uint32_t hi = (uint32_t)(x >> 32);
+    return hi ? 32 + thighest(hi) : thighest((uint32_t)x);
+}
+
+// row_c ^= [c in M1] V1 ^ [c in M2] V2  for every c in M1 | M2 — the one primitive every step of the
+// elimination reduces to.  A single loop (not one per mask) keeps the trip counts of the 32 lanes
+// of a warp close together; words are walked in 32-bit halves from the top bit down (FLO + 2 ops).
+BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2) {
+    uint32_t U = M1 | M2;
+    while (U) {
+        const int c = thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        uint32_t r = J.get(c);
+        if (M1 & b) r ^= V1;
+        if (M2 & b) r ^= V2;
+        J.put(c, r);
+    }
+}
+BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2) {
+#pragma unroll
+    for (int h = 1; h >= 0; h--) {
+        const uint32_t m1 = (uint32_t)(M1 >> (32 * h)), m2 = (uint32_t)(M2 >> (32 * h));
+        uint32_t U = m1 | m2;
+        while (U) {
+            const int c = thighest(U);
+            const uint32_t b = 1u << c;
+            U ^= b;
+            uint64_t r = J.get(c + 32 * h);
+            if (m1 & b) r ^= V1;
+            if (m2 & b) r ^= V2;
+            J.put(c + 32 * h, r);
+        }
+    }
+}
+
 // x_i = x'_i + sum_{a in Sp} x'_a.   (bg_device.cuh: basis_change)   Returns the old row i.
 template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, W Sp) {
     const W bi = tbit<W>(i);
     const W Ji = J.get(i);
-    for (W r = Sp; r; r &= r - 1) J.xr(tlowest(r), Ji);                 // row a += row i
-    // column a += column i: rows r whose (updated) entry (r,i) is set.  By symmetry that column is
-    // row i, plus J_ii on the rows of Sp.
+    // row a += row i (a in Sp), then column a += column i: rows r whose (updated) entry (r,i) is
+    // set get ^= Sp.  By symmetry that column is row i, plus J_ii on the rows of Sp.
     const W col = (Ji ^ ((Ji & bi) ? Sp : (W)0)) & f.A;
-    for (W r = col; r; r &= r - 1) J.xr(tlowest(r), Sp);
+    t_xor2(J, Sp, Ji, col, Sp);
     const W d1i = tfill<W>(tget(f.D1, i)), d2i = tfill<W>(tget(f.D2, i));
     f.D2 ^= Sp & (d2i ^ (d1i & f.D1) ^ Ji);
     f.D1 ^= Sp & d1i;
@@ -84,7 +130,7 @@ template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, 
 
 // impose sum_{a in S} x_a = beta, eliminating x_i, i = lowest(S)    (bg_device.cuh: pivot)
 template <typename W> BG_HD void t_pivot(const Rows<W>& J, TF<W>& f, W S, uint32_t beta) {
-    const int i = tlowest(S);
+    const int i = thighest(S);
     const W bi = tbit<W>(i), Sp = S ^ bi;
     const uint32_t d1 = tget(f.D1, i), d2 = tget(f.D2, i);
     const W Ji = t_basis_change<W>(J, f, i, Sp);
@@ -103,7 +149,7 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     W E = A, Js = 0;
     uint32_t Ds = 0;
     if (has_s) {
-        const int s = tlowest(S);
+        const int s = thighest(S);
         const W bs = tbit<W>(s), Sp = S ^ bs;
         Ds = 2u + 4u * tget(f.D2, s);
         if (Sp) t_basis_change<W>(J, f, s, Sp);
@@ -113,7 +159,7 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     W D2 = f.D2;
     uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
     while (E) {
-        const int a = tlowest(E);
+        const int a = thighest(E);
         const W ba = tbit<W>(a);
         const W Ja = J.get(a) & E & ~ba;
         const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
@@ -123,18 +169,15 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
             if (z0 && (z1 || !has_s)) break;
             continue;
         }
-        const int b = tlowest(Ja);
+        const int b = thighest(Ja);
         const W bb = tbit<W>(b);
         const W Jb = J.get(b) & E & ~bb;
         const W rest = E & ~(ba | bb);
         const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
         neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
         const W Jar = Ja & rest, Jbr = Jb & rest;
-        const W both = Jar & Jbr, onlyA = Jar ^ both, onlyB = Jbr ^ both, JJ = Jar ^ Jbr;
-        for (W r = onlyA; r; r &= r - 1) J.xr(tlowest(r), Jbr);         // J_c[a] only
-        for (W r = onlyB; r; r &= r - 1) J.xr(tlowest(r), Jar);         // J_c[b] only
-        for (W r = both; r; r &= r - 1) J.xr(tlowest(r), JJ);           // both
-        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ both;
+        t_xor2(J, Jar, Jbr, Jbr, Jar);                                  // J_c ^= [J_ca] J_b ^ [J_cb] J_a
+        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
         Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
         E = rest;
     }
@@ -179,7 +222,7 @@ BG_HD bool t_constraints(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, W mrg
 #pragma unroll
         for (int q = 0; q < TPP_MAXC; q++) {            // substitute the pivots of checks q < j, in order
             if (q >= j) break;
-            if (w & (hs[q] & (~hs[q] + 1))) { w ^= hs[q]; beta ^= (hb >> q) & 1u; }
+            if (hs[q] && tget(w, thighest(hs[q]))) { w ^= hs[q]; beta ^= (hb >> q) & 1u; }
         }
         w &= f.A;
         hs[j] = w;                                       // 0 when the check is already implied
@@ -194,6 +237,7 @@ BG_HD bool t_constraints(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, W mrg
 template <typename W>
 BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
     const int t = sh.t;
+#pragma unroll 8
     for (int q = 0; q < t; q++) J.put(q, sh.J[q]);
     TF<W> f;
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
@@ -217,9 +261,10 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
     TF<W> f;
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
     f.A = maskt & ~last;
-    for (W r = mrg; r; r &= r - 1) {                    // x_{2j} = x_{2j+1}
+    for (W r = mrg; r; r &= r - 1) {                    // x_{2j} = x_{2j+1}: eliminate x_{2j}
         const int i = tlowest(r);
-        t_pivot<W>(J, f, tbit<W>(i) | tbit<W>(i + 1), 0u);
+        t_basis_change<W>(J, f, i, tbit<W>(i + 1));
+        f.A &= ~tbit<W>(i);
     }
     const int k2 = t - tpopc(mrg) - tpopc(last);
     if (!t_constraints<W>(J, f, sh, mrg)) { eps = 0; p = 0; m = 0; return; }

@@ -67,10 +67,11 @@ def _terms(cfg, L, oracle):
     return [oracle.Lbits(i, L) for i in range(1 << len(L))]
 
 
+@pytest.mark.parametrize("tpp", [False, True], ids=["warp_per_pair", "thread_per_pair"])
 @pytest.mark.parametrize("stream,k,ns", [("htstack_t4.txt", 0, 24), ("hs_t16_bit6.txt", 0, 3),
                                          ("hs_t40_k9_bit0.txt", 5, 3), ("phase_estimation_q0.txt", 4, 3),
                                          ("toffoli_q0.txt", 0, 2)])
-def test_L_chi_loop_vs_oracle(emu, oracle, stream, k, ns):
+def test_L_chi_loop_vs_oracle(emu, oracle, stream, k, ns, tpp):
     cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
     t, exact = cfg["t"], cfg["exact"]
     rs = np.random.RandomState(3)
@@ -80,7 +81,7 @@ def test_L_chi_loop_vs_oracle(emu, oracle, stream, k, ns):
         for s in range(ns):
             th = oracle.random_state_philox(t, 7, 0, s)
             want = oracle.sample_from_theta(th, P, exact, L)
-            got = emu.terms(th, P, 1, exact, t, terms)
+            got = emu.terms(th, P, 1, exact, t, terms, tpp=tpp)
             assert got["alive"] == want["alive"]
             if not want["alive"]:
                 continue
