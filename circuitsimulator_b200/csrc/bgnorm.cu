@@ -72,7 +72,9 @@ struct PrepArgs {
 struct PairArgs {
     const SampleRec* recs;
     int n_samples;
-    const uint64_t* terms;
+    const uint64_t* terms;   // the chi terms, SORTED by popcount so that the 32 terms a warp takes together
+                             // have active sets of (nearly) equal size; sums are exact integers, order-free
+    const int32_t* term_nat; // natural index i of sorted position (epm output, pair ordering of the exact norm)
     int nterms;
     int t;
     int chunk, chunks_per_sample;
@@ -209,12 +211,9 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
         const int c = (int)(item % (unsigned)a.chunks_per_sample);
         const SampleRec* r = &a.recs[idx];
         if (r->alive != ROUTE_WARP) continue;
-        int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
-        long long diag_index = -1;
-        if (a.tri) {                                // exactProjectorWork: pairs (i, j >= i)
-            diag_index = (long long)(a.first + (uint64_t)idx * a.stride);
-            if ((long long)i0 < diag_index) i0 = (int)diag_index;
-        }
+        const int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
+        // exactProjectorWork: sample i meets the terms j >= i (natural indices)
+        const int diag_index = a.tri ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
         Ambient<NS> am;
         am.f.Q = (uint32_t)r->Q; am.f.D1 = (W)r->D1; am.f.D2 = (W)r->D2;
@@ -230,17 +229,19 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
         for (int i = i0; i < i1; i++) {
             const W term = (W)terms[i];
+            const int nat = (a.tri || a.epm) ? a.term_nat[i] : i;
+            if (a.tri && nat < diag_index) continue;
             int e, p, m;
             if (EXACT) term_H<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, am.k1, a.t, term, e, p, m);
             else term_L<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, am.k1, term, e, p, m);
-            if (a.tri && (long long)i != diag_index) zw_add(z2, e, p, m, sh);
+            if (a.tri && nat != diag_index) zw_add(z2, e, p, m, sh);
             else zw_add(z, e, p, m, sh);
             if (a.epm && lane == 0) {
-                int32_t* o = a.epm + ((size_t)idx * a.nterms + i) * 3;
+                int32_t* o = a.epm + ((size_t)idx * a.nterms + nat) * 3;
                 o[0] = e; o[1] = p; o[2] = m & 7;
             }
+            my_pairs++;
         }
-        my_pairs += (unsigned long long)(i1 - i0);
         if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -287,12 +288,8 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
         const int c = (int)(item % (unsigned)a.chunks_per_sample);
         const SampleRec* r = &a.recs[idx];
         if (r->alive != ROUTE_TPP) continue;
-        int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
-        long long diag_index = -1;
-        if (TRI) {
-            diag_index = (long long)(a.first + (uint64_t)idx * a.stride);
-            if ((long long)i0 < diag_index) i0 = (int)diag_index;
-        }
+        const int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
+        const int diag_index = TRI ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
         __syncwarp();
         for (int q = lane; q < t; q += 32) s_amb[q] = (W)r->J[q];
@@ -321,20 +318,21 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
         for (int g = i0; g < i1; g += 32) {
             const int i = g + lane;
-            if (i < i1) {
+            const int nat = (i < i1 && (TRI || a.epm)) ? a.term_nat[i] : i;
+            if (i < i1 && !(TRI && nat < diag_index)) {
                 const W term = (W)terms[i];
                 int e, p, m;
                 if (EXACT) t_term_H<W>(rows, sh, term, e, p, m);
                 else t_term_L<W>(rows, sh, term, e, p, m);
-                if (TRI && (long long)i != diag_index) zw_add(z2, e, p, m, sh_);
+                if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
                 else zw_add(z, e, p, m, sh_);
                 if (a.epm) {
-                    int32_t* o = a.epm + ((size_t)idx * a.nterms + i) * 3;
+                    int32_t* o = a.epm + ((size_t)idx * a.nterms + nat) * 3;
                     o[0] = e; o[1] = p; o[2] = m & 7;
                 }
+                my_pairs++;
             }
         }
-        my_pairs += (unsigned long long)(i1 - i0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
 #pragma unroll
@@ -351,6 +349,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
             }
         }
     }
+    for (int d = 16; d > 0; d >>= 1) my_pairs += __shfl_down_sync(BG_FULL, my_pairs, d);
     if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
 }
 
@@ -471,7 +470,9 @@ struct bg_ctx {
     int t = 0, exact = 1, k = 0;
     std::vector<uint64_t> L;
     std::vector<uint64_t> terms_host;
-    uint64_t* d_terms = nullptr; size_t d_terms_cap = 0;
+    uint64_t* d_terms = nullptr; size_t d_terms_cap = 0;             // natural order
+    uint64_t* d_terms_sorted = nullptr; size_t d_terms_sorted_cap = 0;  // by popcount (pair kernels)
+    int32_t* d_term_nat = nullptr; size_t d_term_nat_cap = 0;
     double* d_cdf = nullptr; int cdf_t = -1;
     // buffers
     SampleRec* d_recs = nullptr; size_t recs_cap = 0;
@@ -558,7 +559,7 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
-    cudaFree(ctx->d_terms); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
+    cudaFree(ctx->d_terms); cudaFree(ctx->d_terms_sorted); cudaFree(ctx->d_term_nat); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
     cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -692,6 +693,20 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
     if (ensure(ctx, &ctx->d_terms, &ctx->d_terms_cap, padded)) return 1;
     CK(cudaMemsetAsync(ctx->d_terms, 0, padded * 8, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_terms, ctx->terms_host.data(), chi * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {   // popcount-sorted copy for the pair kernels (stable: ties keep the natural order)
+        std::vector<int32_t> nat(chi);
+        for (size_t i = 0; i < chi; i++) nat[i] = (int32_t)i;
+        const std::vector<uint64_t>& th = ctx->terms_host;
+        std::stable_sort(nat.begin(), nat.end(), [&](int32_t x, int32_t y) {
+            return __builtin_popcountll(th[x]) > __builtin_popcountll(th[y]); });
+        std::vector<uint64_t> sorted(padded, 0);
+        for (size_t i = 0; i < chi; i++) sorted[i] = th[nat[i]];
+        if (ensure(ctx, &ctx->d_terms_sorted, &ctx->d_terms_sorted_cap, padded)) return 1;
+        if (ensure(ctx, &ctx->d_term_nat, &ctx->d_term_nat_cap, chi)) return 1;
+        CK(cudaMemcpyAsync(ctx->d_terms_sorted, sorted.data(), padded * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_term_nat, nat.data(), chi * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));       // the host vectors go out of scope
+    }
     if (ctx->cdf_t != t) {
         double cdf[BG_MAX_T + 1];
         dimension_cdf(t, cdf);
@@ -800,6 +815,8 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     if (blocks < 1) blocks = 1;
     a.pair_count = ctx->d_counters + 1;
     a.n_warp_routed = ctx->d_counters + 2;
+    a.terms = ctx->d_terms_sorted;
+    a.term_nat = ctx->d_term_nat;
     if (!ctx->force_warp) {
         a.counter = ctx->d_counters;
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
