@@ -10,8 +10,8 @@ Input = the instruction stream the reference's unmodified front end wrote for th
 (tests/golden/streams/hs_t40_k9_bit0.txt; generator: tests/golden/make_fixtures.py).
 One STEP = one probability() back-end evaluation = both projectors (G', H'):
 2 x 2^16 x 512 = 67,108,864 stabilizer inner products (+ the 2 x 2^16 theta draws and projections).
-Samples are sharded by stride across ranks (weak scaling is NOT used: total work is fixed... see
-`scaling`), partial sums are all-reduced over NCCL inside the library.
+Samples are sharded by stride across ranks (total work is fixed: "scaling": "strong"); the partial
+sums are all-reduced over NCCL inside the library.
 
 Prints ONE JSON line (rank 0).
 """
@@ -111,6 +111,16 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def reference_sample(t, exact, k, chi, seconds):
+    """(samples per core, k for the reference, terms per sample) so that one step takes ~`seconds`."""
+    rate = 14.0 if t >= 33 else 700.0          # pairs/s/core of the reference, build container (BASELINE.md)
+    budget = max(1.0, rate * seconds / 2)      # pairs per projector per core
+    if exact or chi <= budget:
+        return max(1, int(budget // chi)), k, chi
+    k_ref = max(1, int(budget).bit_length() - 1)
+    return 1, k_ref, 1 << k_ref
+
+
 def run_reference(args, cfgname):
     """--impl reference: the reference's own C implementation (oracle/_ref/mpibackend_ref, the
     unmodified sources behind a single-rank MPI shim, -O2) on the host cores: one process per core,
@@ -130,12 +140,13 @@ def run_reference(args, cfgname):
     if not os.path.exists(exe):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/mpibackend_ref not built"}))
         return
-    # bounded sample: each core evaluates `per_core` samples of each projector
-    rate_guess = 14.0 if t >= 33 else 700.0            # pairs/s/core measured in the build container
-    per_core = max(1, int(round(rate_guess * 4.0 / (2 * chi))))     # ~4 s per step
+    # bounded sample: every core evaluates `per_core` samples of each projector against `chi_ref`
+    # terms.  For |L> workloads the reference is given a smaller k (its own random L): the cost of
+    # one inner product does not depend on k, and a full 2 x 512-term sample takes it > 70 s per core.
+    per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds=16.0)
     tok = open(os.path.join(STREAMS, stream)).read().split()
     tok[3] = str(per_core)        # samples
-    tok[6] = str(k)               # k
+    tok[6] = str(k_ref)           # k
     tok[7] = str(int(bool(exact)))
     tok[12] = "1"                 # forceSample: stay on the sampled path
     text = "\n".join(tok) + "\n"
@@ -150,13 +161,13 @@ def run_reference(args, cfgname):
             p.stdout.read()
             p.wait()
 
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):      # CPU code: one untimed pass is all the warm-up there is
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    pairs_per_step = cores * per_core * 2 * chi
+    pairs_per_step = cores * per_core * 2 * chi_ref
     value = pairs_per_step * args.steps / dt
     line = {"metric": "stabilizer inner products/sec", "value": value, "unit": "inner products/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -166,8 +177,9 @@ def run_reference(args, cfgname):
                        "samples_per_projector": samples},
             "cpu_baseline": {"value": value, "unit": "inner products/s", "cores": cores, "kind": kind,
                              "sample": "%d processes x %d samples x 2 projectors x %d terms per step "
-                                       "(reference C sources unmodified, gcc -O2, single-rank MPI shim)"
-                                       % (cores, per_core, chi)},
+                                       "(reference C sources unmodified, gcc -O2, single-rank MPI shim; the per-sample "
+                                       "theta draw + projection is amortised over %d instead of %d terms)"
+                                       % (cores, per_core, chi_ref, chi_ref, chi)},
             "e2e": {"value": value, "unit": "inner products/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -187,10 +199,9 @@ def cpu_baseline_leg(cfgname, seconds=12.0):
     cores = os.cpu_count() or 1
     if not os.path.exists(exe):
         return None
-    rate_guess = 14.0 if t >= 33 else 700.0
-    per_core = max(1, int(round(rate_guess * seconds / (2 * chi))))
+    per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds)
     tok = open(os.path.join(STREAMS, stream)).read().split()
-    tok[3], tok[6], tok[7], tok[12] = str(per_core), str(k), str(int(bool(exact))), "1"
+    tok[3], tok[6], tok[7], tok[12] = str(per_core), str(k_ref), str(int(bool(exact))), "1"
     text = ("\n".join(tok) + "\n").encode()
     t0 = time.perf_counter()
     procs = [subprocess.Popen([exe, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
@@ -202,10 +213,10 @@ def cpu_baseline_leg(cfgname, seconds=12.0):
         p.stdout.read()
         p.wait()
     dt = time.perf_counter() - t0
-    pairs = cores * per_core * 2 * chi
+    pairs = cores * per_core * 2 * chi_ref
     return {"value": pairs / dt, "unit": "inner products/s", "cores": cores, "kind": "reference",
             "sample": "%d processes x %d samples x 2 projectors x %d terms in %.1f s (reference C sources "
-                      "unmodified, gcc -O2, single-rank MPI shim)" % (cores, per_core, chi, dt)}
+                      "unmodified, gcc -O2, single-rank MPI shim)" % (cores, per_core, chi_ref, dt)}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -276,23 +287,30 @@ def main():
         den = ctxs[1].sampled_finish(1.0)
         results.append((num, den))
 
+    sampler = ClockSampler(local)
+    sampler.start()                      # samples through warm-up + timed region (all under the same load)
     for _ in range(max(3, args.warmup)):
         step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches = 0.0, 0
+    kernel_ms, prepare_ms, pairs_ms, launches = 0.0, 0.0, 0.0, 0
     e0.record(tstream)
     for _ in range(args.steps):
         step_resident()
         for c in ctxs:
             st = c.stats()
             kernel_ms += st["kernel_ms"]
+            prepare_ms += st["prepare_ms"]
+            pairs_ms += st["pairs_ms"]
             launches += st["launches"]
     e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
+    # a timed region of a few ms is shorter than one nvidia-smi poll: keep the same load running
+    # (untimed) until the sampler has at least 3 rows
+    hold = time.perf_counter()
+    while len(sampler.rows) < 3 and time.perf_counter() - hold < 4.0:
+        step_resident()
     sampler.stop_flag = True
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -322,33 +340,33 @@ def main():
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = pairs_per_step * args.steps / float(tw.item())
-    h2d = 2 * (chi * 8 + (t + 1) * 8 * 0 + 2 * 1024 + 2 * 128 + 8)   # terms table + bg_projector struct, per projector
     import ctypes
-    h2d = 2 * (chi * 8 + ctypes.sizeof(bg.Projector))
+    h2d = 2 * (chi * 8 + ctypes.sizeof(bg.Projector))      # terms table + bg_projector, per projector
     d2h = 2 * 8
 
     if rank == 0:
-        # algorithmic lane-ops per inner product: see DESIGN.md section "Roofline"
-        W = {"hidden_shift_n40_t40_k9_L65536": None}.get(cfgname)
         clocks = sampler.summary()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        work = json.load(open(os.path.join(ROOT, "profiles", "work_model.json"))) if os.path.exists(
-            os.path.join(ROOT, "profiles", "work_model.json")) else {}
-        wm = work.get(cfgname, {})
-        lane_ops = wm.get("alu_lane_ops_per_pair")
-        per_launch_pairs = samples * chi / world
-        k_ms = kernel_ms / max(1, args.steps * 2)
+        wpath = os.path.join(ROOT, "profiles", "work_model.json")
+        wm = json.load(open(wpath)).get(cfgname, {}) if os.path.exists(wpath) else {}
+        lane_ops = wm.get("alu_lane_ops_per_pair")           # DESIGN.md "Roofline": algorithmic lane-ops / pair
+        per_launch_pairs = samples * chi / world             # one k_pairs_tpp launch = one projector on this rank
+        k_ms = pairs_ms / max(1, args.steps * 2)             # CUDA events around the pair kernels, per launch
         roof = {"bound": "int_alu", "unit": "Tlaneop/s",
-                "peak": lop3_peak / 1e12, "peak_source": "bg_measure_int_peak (LOP3 microbenchmark, this run)",
+                "kernel": "k_pairs_tpp", "kernel_ms": k_ms, "kernel_share_of_step": 2 * k_ms / (ms / args.steps),
+                "prepare_ms": prepare_ms / max(1, args.steps * 2),
+                "achieved": (per_launch_pairs * lane_ops / (k_ms * 1e-3) / 1e12) if lane_ops and k_ms > 0 else None,
+                "peak": lop3_peak / 1e12,
+                "peak_source": "LOP3 lane-ops/s measured in this run by bg_measure_int_peak (64 lanes/clk/SM x 148 SMs)",
                 "popc_peak": popc_peak / 1e12,
-                "kernel_ms_per_projector": k_ms,
-                "achieved": (per_launch_pairs * lane_ops / (k_ms * 1e-3) / 1e12) if lane_ops else None,
                 "lane_ops_per_pair": lane_ops,
+                "pipe_busy_ncu": wm.get("alu_pipe_busy_pct"), "active_lanes_ncu": wm.get("active_lanes_per_inst"),
                 "traffic": wm.get("dram_bytes_per_launch"),
+                "hbm_gbs_achieved": (wm.get("dram_bytes_per_launch") / (k_ms * 1e-3) / 1e9) if wm.get("dram_bytes_per_launch") and k_ms > 0 else None,
                 "hbm_gbs_peak": peaks.get("hbm_gbs")}
         roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["achieved"] else None
         line = {"metric": "stabilizer inner products/sec", "value": value, "unit": "inner products/s",
@@ -358,8 +376,11 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": cfgname, "description": desc, "t": t, "chi": chi,
                            "samples_per_projector": samples, "projectors": 2,
-                           "l2": "per-sample records (2 x %.0f MB) exceed nothing: the kernel is ALU-bound; "
-                                 "inputs regenerated every step from the counter-based RNG" % (samples * 1072 / 1e6)},
+                           "step": "one probability() back-end evaluation: both projectors, theta draw + projection + "
+                                   "L x chi inner products + reduction (+ NCCL all-reduce for n_gpus > 1)",
+                           "l2": "inputs are regenerated every step from the counter-based RNG; the per-sample "
+                                 "records written and re-read each step (2 x %.0f MB) exceed the 126 MB L2"
+                                 % (samples * 1072 / 1e6)},
                 "e2e": {"value": e2e_value, "unit": "inner products/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,

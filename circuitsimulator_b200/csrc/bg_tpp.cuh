@@ -18,6 +18,16 @@
 #pragma once
 #include "bg_device.cuh"
 
+// Work accounting (CPU build of this header only, -DBG_COUNT_WORK): the algorithm's own operation
+// counts, from which DESIGN.md's "algorithmic lane-ops per inner product" is computed.
+#if defined(BG_COUNT_WORK) && !defined(__CUDACC__)
+struct BgWork { unsigned long long xors, rows, dimers, monomers, basis_changes, pairs; };
+extern BgWork g_bg_work;
+#define BG_WORK(field, n) (g_bg_work.field += (n))
+#else
+#define BG_WORK(field, n) ((void)0)
+#endif
+
 namespace bg {
 
 // per-thread view of its working rows: row r lives at base[r * stride]
@@ -95,6 +105,7 @@ BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
         if (M1 & b) r ^= V1;
         if (M2 & b) r ^= V2;
         J.put(c, r);
+        BG_WORK(rows, 1); BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0));
     }
 }
 BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2) {
@@ -110,6 +121,7 @@ BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2
             if (m1 & b) r ^= V1;
             if (m2 & b) r ^= V2;
             J.put(c + 32 * h, r);
+            BG_WORK(rows, 1); BG_WORK(xors, ((m1 & b) ? 1 : 0) + ((m2 & b) ? 1 : 0));
         }
     }
 }
@@ -122,6 +134,7 @@ template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, 
     // set get ^= Sp.  By symmetry that column is row i, plus J_ii on the rows of Sp.
     const W col = (Ji ^ ((Ji & bi) ? Sp : (W)0)) & f.A;
     t_xor2(J, Sp, Ji, col, Sp);
+    BG_WORK(basis_changes, 1);
     const W d1i = tfill<W>(tget(f.D1, i)), d2i = tfill<W>(tget(f.D2, i));
     f.D2 ^= Sp & (d2i ^ (d1i & f.D1) ^ Ji);
     f.D1 ^= Sp & d1i;
@@ -166,6 +179,7 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
         if (Ja == 0) {
             z0 |= d2a; z1 |= d2a ^ sa; cnt++;
             E ^= ba;
+            BG_WORK(monomers, 1);
             if (z0 && (z1 || !has_s)) break;
             continue;
         }
@@ -176,6 +190,7 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
         const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
         neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
         const W Jar = Ja & rest, Jbr = Jb & rest;
+        BG_WORK(dimers, 1);
         t_xor2(J, Jar, Jbr, Jbr, Jar);                                  // J_c ^= [J_ca] J_b ^ [J_cb] J_a
         D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
         Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));

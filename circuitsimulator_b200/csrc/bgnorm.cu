@@ -461,7 +461,7 @@ struct bg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evp2 = nullptr;
     int sm_count = 0;
     int rank = 0, world = 1;
     bool allreduce = true;
@@ -489,6 +489,7 @@ struct bg_ctx {
     bg_projector P_host;
     uint64_t samples = 0; int bins = 1; uint64_t seed = 0;
     bool prepared = false;
+    bool phase_events = false;
     std::vector<double> bin_sums;
     bg_stats stats;
     std::string err;
@@ -541,6 +542,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaStreamCreate failed"); }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->evp0); cudaEventCreate(&ctx->evp1); cudaEventCreate(&ctx->evp2);
     if (cudaMalloc((void**)&ctx->d_P, sizeof(bg_projector)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 8 * sizeof(double)) != cudaSuccess ||
@@ -563,6 +565,7 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evp0) { cudaEventDestroy(ctx->evp0); cudaEventDestroy(ctx->evp1); cudaEventDestroy(ctx->evp2); }
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -890,12 +893,16 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
     pa.seed = ctx->seed; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
     pa.cdf = ctx->d_cdf;
+    CK(cudaEventRecord(ctx->evp0, ctx->stream));
     if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
+    CK(cudaEventRecord(ctx->evp1, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
     PairArgs qa; memset(&qa, 0, sizeof qa);
     qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
     qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
     if (launch_pairs(ctx, qa)) return 1;
+    CK(cudaEventRecord(ctx->evp2, ctx->stream));
+    ctx->phase_events = true;
     k_finalize_sampled<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per);
     k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red + red_slot);
     CK(cudaGetLastError());
@@ -930,6 +937,13 @@ static int collect_stats(bg_ctx* ctx) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms = ms;
+    ctx->stats.prepare_ms = ctx->stats.pairs_ms = 0;
+    if (ctx->phase_events) {
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, ctx->evp0, ctx->evp1) == cudaSuccess) ctx->stats.prepare_ms = a;
+        if (cudaEventElapsedTime(&b, ctx->evp1, ctx->evp2) == cudaSuccess) ctx->stats.pairs_ms = b;
+        ctx->phase_events = false;
+    }
     unsigned long long c[2];
     CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.pairs = c[1];

@@ -161,6 +161,8 @@ typedef struct bg_stats {
     uint64_t launches;         /* kernels launched by the last call                               */
     uint64_t h2d_bytes;        /* host->device bytes moved by the last call                       */
     uint64_t d2h_bytes;        /* device->host bytes moved by the last call                       */
+    double   prepare_ms;       /* ... of which k_prepare (theta draw + projection + ambient form)  */
+    double   pairs_ms;         /* ... of which the pair kernels (the L x chi loop proper)          */
 } bg_stats;
 int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
 

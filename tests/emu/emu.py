@@ -49,6 +49,7 @@ class Emu:
         lib.emu_measure_pauli.restype = C.c_int
         lib.emu_random_state.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(State),
                                          _P(C.c_uint64)]
+        lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
         self.lib = lib
 
     def inner_product(self, a, b):
@@ -67,6 +68,11 @@ class Emu:
                                    u64_array(terms), epm.ctypes.data_as(_P(C.c_int32)), C.byref(npf),
                                    C.byref(k), zw)
         return dict(alive=alive, epm=epm, npf=npf.value, k=k.value, zw=list(zw))
+
+    def work_counters(self, reset=True):
+        out = (C.c_ulonglong * 6)()
+        self.lib.emu_work_counters(out, int(reset))
+        return dict(zip(["xors", "rows", "dimers", "monomers", "basis_changes", "pairs"], [int(v) for v in out]))
 
     def measure_pauli(self, s, m, zeta, xi):
         """returns (code, state in contiguous layout); code 0 annihilated, 1 unchanged, 2 factor 2^-1/2"""

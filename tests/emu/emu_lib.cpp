@@ -1,5 +1,6 @@
 // emu_lib.cpp — TEST INFRASTRUCTURE: runs the product's warp-level device code
 // (circuitsimulator_b200/csrc/bg_device.cuh, bg_philox.cuh) on the CPU warp emulator.
+#define BG_COUNT_WORK 1
 #include "cpu_warp.h"
 #include "bg_device.cuh"
 #include "bg_warp_ops.cuh"
@@ -43,6 +44,7 @@ void run(const std::function<void()>& body) {
 }
 }  // namespace emu
 
+BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
 using namespace bg;
 
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
@@ -83,6 +85,7 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
             if (exact) t_term_H<W>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W>(rows, sh, (W)terms[i], e, p, m);
+            g_bg_work.pairs++;
             zw_add(z, e, p, m, t / 2 + 1);
             if (epm) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m; }
         }
@@ -119,6 +122,12 @@ int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int
                   const uint64_t* terms, int32_t* epm, int* npf_out, int* k_out, long long* zw_out) {
     if (t <= 32) return terms_tpp<1>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
     return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
+}
+
+void emu_work_counters(unsigned long long* out, int reset) {
+    out[0] = g_bg_work.xors; out[1] = g_bg_work.rows; out[2] = g_bg_work.dimers; out[3] = g_bg_work.monomers;
+    out[4] = g_bg_work.basis_changes; out[5] = g_bg_work.pairs;
+    if (reset) g_bg_work = BgWork{0, 0, 0, 0, 0, 0};
 }
 
 int emu_measure_pauli(bg_state* st, uint64_t* A, int m, uint64_t zeta, uint64_t xi) {
