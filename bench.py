@@ -35,6 +35,11 @@ CONFIGS = {
     "hidden_shift_n40_t16_L16384": ("hs_t16_bit6.txt", 16384, 0,
                                     "random hidden-shift n=40, t=16 T gates, exact |H^t> (chi=256), L=2^14"),
     "htstack_t4_L1024": ("htstack_t4.txt", 1024, 0, "HTstack.circ output 0, t=4 (chi=4), L=1024"),
+    # BASELINE configs[4], second half: synthetic t=60 sweep (60-bit states in 64-bit rows), theta from the
+    # device RNG, phi from prepL, random Hermitian Pauli projectors with 40 / 39 generators
+    "synthetic_t60_k8_L65536": (None, 65536, 8, "synthetic t=60, |L> k=8 (chi=256), L=2^16"),
+    "synthetic_t60_k12_L65536": (None, 65536, 12, "synthetic t=60, |L> k=12 (chi=4096), L=2^16"),
+    "synthetic_t60_k16_L16384": (None, 16384, 16, "synthetic t=60, |L> k=16 (chi=65536), L=2^14"),
 }
 DEFAULT_CONFIG = "hidden_shift_n40_t40_k9_L65536"
 
@@ -65,6 +70,45 @@ def parse_stream(path):
             zs.append(z)
         projs.append((nq, ph, xs, zs))
     return cfg, projs[0], projs[1]
+
+
+def synthetic_stream(t=60, nstabs=(40, 39), seed=60):
+    """A synthetic back-end input: random Hermitian Pauli generators i^m Z(z) X(x), m = |x & z| mod 2 (+2)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    cfg = {"t": t, "exact": 0, "k": 0}
+    projs = []
+    for ns in nstabs:
+        ph, xs, zs = [], [], []
+        for _ in range(ns):
+            x = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) if rs.randint(0, 2) else 0
+            z = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1)
+            ph.append((bin(x & z).count("1") + 2 * int(rs.randint(0, 2))) % 4)
+            xs.append(x)
+            zs.append(z)
+        projs.append((t, ph, xs, zs))
+    return cfg, projs[0], projs[1]
+
+
+def load_config(cfgname):
+    stream, samples, k, desc = CONFIGS[cfgname]
+    if stream is None:
+        cfg, G, H = synthetic_stream()
+    else:
+        cfg, G, H = parse_stream(os.path.join(STREAMS, stream))
+    return cfg, G, H, samples, k, desc
+
+
+def stream_text(t, samples, k, exact, G, H):
+    """The token stream of libcirc/probability.py:247-272 for this input (forceSample on)."""
+    tok = [0, 0, 0, samples, 1, t, k, int(bool(exact)), 1e-05, 0, 0, 0, 1]
+    for (nq, ph, xs, zs) in (G, H):
+        tok += [len(ph), nq if ph else 0]
+        for p_, x, z in zip(ph, xs, zs):
+            tok.append(p_)
+            for q in range(nq):
+                tok += [(x >> q) & 1, (z >> q) & 1]
+    return "\n".join(str(v) for v in tok) + "\n"
 
 
 def fixed_L(k, t):
@@ -129,8 +173,7 @@ def run_reference(args, cfgname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    stream, samples, k, desc = CONFIGS[cfgname]
-    cfg, G, H = parse_stream(os.path.join(STREAMS, stream))
+    cfg, G, H, samples, k, desc = load_config(cfgname)
     t = cfg["t"]
     exact = cfg["exact"] if k == 0 else 0
     chi = (1 << ((t + 1) // 2)) if exact else (1 << k)
@@ -144,12 +187,7 @@ def run_reference(args, cfgname):
     # terms.  For |L> workloads the reference is given a smaller k (its own random L): the cost of
     # one inner product does not depend on k, and a full 2 x 512-term sample takes it > 70 s per core.
     per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds=16.0)
-    tok = open(os.path.join(STREAMS, stream)).read().split()
-    tok[3] = str(per_core)        # samples
-    tok[6] = str(k_ref)           # k
-    tok[7] = str(int(bool(exact)))
-    tok[12] = "1"                 # forceSample: stay on the sampled path
-    text = "\n".join(tok) + "\n"
+    text = stream_text(t, per_core, k_ref, exact, G, H)
 
     def step():
         procs = [subprocess.Popen([exe, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
@@ -190,8 +228,7 @@ def cpu_baseline_leg(cfgname, seconds=12.0):
     cores for a bounded sample."""
     class A:
         pass
-    stream, samples, k, desc = CONFIGS[cfgname]
-    cfg, G, H = parse_stream(os.path.join(STREAMS, stream))
+    cfg, G, H, samples, k, desc = load_config(cfgname)
     t = cfg["t"]
     exact = cfg["exact"] if k == 0 else 0
     chi = (1 << ((t + 1) // 2)) if exact else (1 << k)
@@ -200,9 +237,7 @@ def cpu_baseline_leg(cfgname, seconds=12.0):
     if not os.path.exists(exe):
         return None
     per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds)
-    tok = open(os.path.join(STREAMS, stream)).read().split()
-    tok[3], tok[6], tok[7], tok[12] = str(per_core), str(k_ref), str(int(bool(exact))), "1"
-    text = ("\n".join(tok) + "\n").encode()
+    text = stream_text(t, per_core, k_ref, exact, G, H).encode()
     t0 = time.perf_counter()
     procs = [subprocess.Popen([exe, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
                               stderr=subprocess.DEVNULL) for _ in range(cores)]
@@ -247,8 +282,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    stream, samples, k, desc = CONFIGS[cfgname]
-    cfg, Gd, Hd = parse_stream(os.path.join(STREAMS, stream))
+    cfg, Gd, Hd, samples, k, desc = load_config(cfgname)
     t = cfg["t"]
     exact = cfg["exact"] if k == 0 else 0
     L = [] if exact else fixed_L(k, t)

@@ -481,6 +481,7 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
+    int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
@@ -551,6 +552,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
+    if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
     *out = ctx;
@@ -786,7 +788,7 @@ template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const Pair
 template <typename W, bool EXACT, bool TRI> static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pairs_tpp<W, EXACT, TRI><<<blocks, 32 * WARPS_PER_BLOCK, smem, ctx->stream>>>(a);
+    k_pairs_tpp<W, EXACT, TRI><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     return 0;
@@ -824,9 +826,14 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         a.counter = ctx->d_counters;
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;
-        const size_t smem = (size_t)a.smem_terms * 8 + (size_t)WARPS_PER_BLOCK * a.t * wb + (size_t)a.t * 32 * WARPS_PER_BLOCK * wb;
-        if (a.t <= 32) { if (launch_tpp_w<uint32_t>(ctx, a, (int)blocks, smem)) return 1; }
-        else { if (launch_tpp_w<uint64_t>(ctx, a, (int)blocks, smem)) return 1; }
+        const int tw = ctx->tpp_warps;
+        const size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb;
+        long long tb = (long long)ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK / tw;
+        const long long tneed = (long long)((items + tw - 1) / tw);
+        if (tb > tneed) tb = tneed;
+        if (tb < 1) tb = 1;
+        if (a.t <= 32) { if (launch_tpp_w<uint32_t>(ctx, a, (int)tb, smem)) return 1; }
+        else { if (launch_tpp_w<uint64_t>(ctx, a, (int)tb, smem)) return 1; }
     }
     a.counter = ctx->d_counters + 3;
     a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;

@@ -248,3 +248,119 @@ def test_full_size_config4_properties(be):
         be.set_allreduce(True)
     assert abs(sum(parts) - a) <= 1e-13 * abs(a)
     assert a > 0
+
+
+# ----------------------------------------------------------------------------- edge cases
+def _random_projector(rs, t, n):
+    import circuitsimulator_b200 as bg
+    ph, xs, zs = [], [], []
+    for _ in range(n):
+        x = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) if rs.randint(0, 2) else 0
+        z = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1)
+        if t > 62:
+            x |= int(rs.randint(0, 4)) << 62 if x else 0
+            z |= int(rs.randint(0, 4)) << 62
+        ph.append((bin(x & z).count("1") + 2 * int(rs.randint(0, 2))) % 4)      # Hermitian
+        xs.append(x)
+        zs.append(z)
+    return bg.Projector.make(t, ph, xs, zs), OProj.make(t, ph, xs, zs)
+
+
+@pytest.mark.parametrize("t,k,nst,samples", [(1, 1, 1, 64), (2, 2, 2, 64), (7, 3, 5, 48), (31, 5, 20, 24),
+                                             (32, 5, 20, 24), (33, 5, 20, 16), (60, 6, 40, 10), (64, 6, 50, 10),
+                                             (64, 5, 128, 8)])
+def test_widths_and_generator_counts_vs_oracle(be, oracle, t, k, nst, samples):
+    """State widths 1..64 (both word sizes, the 32/33 boundary, the full 64-bit row), up to the
+    maximum of 128 generators; |L> decomposition with random L."""
+    rs = np.random.RandomState(100 + t + nst)
+    P, OP = _random_projector(rs, t, nst)
+    L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) | ((int(rs.randint(0, 4)) << 62) if t > 62 else 0) for _ in range(k)]
+    be.set_decomposition(t, False, L)
+    got = be.sampled_norm(P, samples, 1, 77, 1.0)
+    tot, per = oracle.sampled_sum_philox(OP, False, L, 77, 0, 0, 1, samples)
+    want = tot / samples
+    assert abs(got - want) <= 1e-11 * abs(want) + 1e-300, (got, want)
+
+
+@pytest.mark.parametrize("t", [3, 8, 11, 16])
+def test_exact_decomposition_odd_and_even_t(be, oracle, t):
+    rs = np.random.RandomState(t)
+    P, OP = _random_projector(rs, t, t // 2 + 1)
+    be.set_decomposition(t, True)
+    got = be.sampled_norm(P, 40, 1, 5, 1.0)
+    tot, _ = oracle.sampled_sum_philox(OP, True, [], 5, 0, 0, 1, 40)
+    assert abs(got - tot / 40) <= 1e-11 * abs(tot / 40) + 1e-300
+    assert abs(be.exact_norm(P, 1.0) - oracle.exact_projector(OP, True, [], 1.0)) <= 1e-11
+
+
+def test_low_dimensional_thetas_take_the_warp_kernel(be, oracle):
+    """Thetas with many parity checks (k << t) are routed to the warp-per-pair kernel; host-supplied
+    thetas of every dimension, including k = 0, must agree with the oracle."""
+    t = 12
+    rs = np.random.RandomState(3)
+    L = [int(rs.randint(0, 1 << t)) for _ in range(4)]
+    be.set_decomposition(t, False, L)
+    thetas = []
+    for j in range(40):
+        s = oracle.random_state_philox(t, 9, 0, j)
+        for _ in range(j % (t + 1)):                       # cut the dimension down by measuring Z-type Paulis
+            oracle.measure_pauli(s, 0, int(rs.randint(1, 1 << t)), 0)
+        thetas.append(s)
+    import circuitsimulator_b200 as bg
+    empty = bg.Projector.make(t, [], [], [])
+    out = be.sampled_norm_from_states(empty, states_to_numpy(thetas), project=False, want_epm=True, chi=16)
+    ks = set()
+    for j, s in enumerate(thetas):
+        ks.add(s.k)
+        for i in range(16):
+            want = oracle.inner_product(s, oracle.prepL(i, t, L))
+            assert epm_equal(tuple(out["epm"][j, i]), want), (j, i, s.k)
+    assert min(ks) <= 2 and max(ks) >= 10
+
+
+def test_many_terms_not_staged_in_shared_memory(be, oracle):
+    """chi = 4096 > the staged-table limit: terms are read from global memory."""
+    t, k = 20, 12
+    rs = np.random.RandomState(8)
+    P, OP = _random_projector(rs, t, 9)
+    L = [int(rs.randint(0, 1 << t)) for _ in range(k)]
+    be.set_decomposition(t, False, L)
+    got = be.sampled_norm(P, 6, 1, 1, 1.0)
+    tot, _ = oracle.sampled_sum_philox(OP, False, L, 1, 0, 0, 1, 6)
+    assert abs(got - tot / 6) <= 1e-11 * abs(tot / 6) + 1e-300
+
+
+def test_closed_forms_and_errors(be):
+    import circuitsimulator_b200 as bg
+    be.set_decomposition(4, True)
+    assert be.sampled_norm(bg.Projector.make(4, [], [], []), 10, 1, 0, 1.5) == 1.5 ** 2      # innerprod.c:47
+    assert be.exact_norm(bg.Projector.make(4, [], [], []), 1.5) == 1.5 ** 2                  # innerprod.c:150
+    with pytest.raises(bg.BGError):
+        be.sampled_norm(bg.Projector.make(5, [0], [1], [0]), 10, 1, 0, 1.0)                  # width mismatch
+    with pytest.raises(bg.BGError):
+        be.set_decomposition(65, True)
+    with pytest.raises(bg.BGError):
+        be.set_decomposition(10, False, [1] * 30)                                            # k > 26
+    # more shards than samples: some ranks own nothing
+    be.set_allreduce(False)
+    try:
+        parts = []
+        for r in range(4):
+            be.set_shard(r, 4)
+            parts.append(be.sampled_norm(bg.Projector.make(4, [0], [3], [5]), 3, 1, 2, 1.0))
+    finally:
+        be.set_shard(0, 1)
+        be.set_allreduce(True)
+    whole = be.sampled_norm(bg.Projector.make(4, [0], [3], [5]), 3, 1, 2, 1.0)
+    assert abs(sum(parts) - whole) < 1e-15 and parts[3] == 0.0
+
+
+def test_bins_median_of_means(be, oracle):
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "htstack_t4.txt"))
+    be.set_decomposition(4, True)
+    got = be.sampled_norm(to_bg(G), 50, 3, 21, 1.0)
+    means = [oracle.sampled_sum_philox(G, True, [], 21, b, 0, 1, 50)[0] / 50 for b in range(3)]
+    # the reference's comparator truncates differences to int (innerprod.c:17-19): values within 1 of each
+    # other compare equal, so which of them qsort leaves in the middle is libc's business — the result is
+    # one of the bin means, bit for bit what the reference's qsort call would pick from the same values
+    assert min(abs(got - m) for m in means) < 1e-12
