@@ -73,7 +73,10 @@ def parse_stream(path):
 
 
 def synthetic_stream(t=60, nstabs=(40, 39), seed=60):
-    """A synthetic back-end input: random Hermitian Pauli generators i^m Z(z) X(x), m = |x & z| mod 2 (+2)."""
+    """A synthetic back-end input: random Hermitian Pauli generators i^m Z(z) X(x), m = |x & z| mod 2 (+2),
+    every one with a non-trivial X part — like the gadgetized-T projectors of real circuits (the hidden-shift
+    and phase-estimation streams keep dim K(theta) within ~3 of t after projection); Z-only generators would
+    each cut the dimension by one instead."""
     import numpy as np
     rs = np.random.RandomState(seed)
     cfg = {"t": t, "exact": 0, "k": 0}
@@ -81,7 +84,7 @@ def synthetic_stream(t=60, nstabs=(40, 39), seed=60):
     for ns in nstabs:
         ph, xs, zs = [], [], []
         for _ in range(ns):
-            x = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) if rs.randint(0, 2) else 0
+            x = (int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1)) | 1
             z = int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1)
             ph.append((bin(x & z).count("1") + 2 * int(rs.randint(0, 2))) % 4)
             xs.append(x)

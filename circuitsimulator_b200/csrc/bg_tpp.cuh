@@ -216,9 +216,11 @@ template <typename W> struct TShared {
     W D1, D2;
     uint32_t Q;
     int k1, t;
-    int ncons;           // parity checks (t - k1), <= TPP_MAXC
-    W cw[TPP_MAXC];
-    uint32_t cbeta;      // bit j = right-hand side of check j
+    int ncons;           // parity checks (t - k1)
+    W cw[TPP_MAXC];      // the checks when ncons <= TPP_MAXC (register copy)
+    uint32_t cbeta;      // bit j = right-hand side of check j (ncons <= TPP_MAXC)
+    const W* cwv;        // all checks (shared memory) and their right-hand sides, any ncons <= t
+    W cbetav;
 };
 
 // membership checks of K_theta, restricted to this term's active set.  Earlier pivots are
@@ -248,8 +250,35 @@ BG_HD bool t_constraints(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, W mrg
     return true;
 }
 
-// <phi|theta> for a |L> term (prepL): |+> on supp(xt), |0> elsewhere.
+// Same with any number of checks: the pivot history lives in the thread's own rows t .. t+ncons-1
+// (shared memory) instead of registers.  A check only needs rewriting when it contains a variable
+// eliminated by an earlier check (mask `gone`).
 template <typename W>
+BG_HD bool t_constraints_many(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, W mrg) {
+    const int t = sh.t;
+    W hb = 0, gone = 0;
+    for (int j = 0; j < sh.ncons; j++) {
+        W w = sh.cwv[j];
+        w ^= (w & mrg) << 1;
+        uint32_t beta = tget(sh.cbetav, j);
+        if (w & gone) {
+            for (int q = 0; q < j; q++) {
+                const W hq = J.get(t + q);
+                if (hq && tget(w, thighest(hq))) { w ^= hq; beta ^= tget(hb, q); }
+            }
+        }
+        w &= f.A;
+        J.put(t + j, w);
+        hb |= (W)beta << j;
+        if (w == 0) { if (beta) return false; continue; }
+        gone |= tbit<W>(thighest(w));
+        t_pivot<W>(J, f, w, beta);
+    }
+    return true;
+}
+
+// <phi|theta> for a |L> term (prepL): |+> on supp(xt), |0> elsewhere.
+template <typename W, bool MANYC = false>
 BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
     const int t = sh.t;
 #pragma unroll 8
@@ -258,13 +287,13 @@ BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int&
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
     f.A = xt & tlowmask<W>(t);
     const int k2 = tpopc(f.A);
-    if (!t_constraints<W>(J, f, sh, (W)0)) { eps = 0; p = 0; m = 0; return; }
+    if (!(MANYC ? t_constraints_many<W>(J, f, sh, (W)0) : t_constraints<W>(J, f, sh, (W)0))) { eps = 0; p = 0; m = 0; return; }
     t_expsum<W>(J, f, eps, p, m);
     if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
 }
 
 // <phi|theta> for a |H^t> term (prepH); e1 as in bg_device.cuh: term_H.
-template <typename W>
+template <typename W, bool MANYC = false>
 BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int& p, int& m) {
     const int t = sh.t;
     const W maskt = tlowmask<W>(t);
@@ -282,7 +311,7 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
         f.A &= ~tbit<W>(i);
     }
     const int k2 = t - tpopc(mrg) - tpopc(last);
-    if (!t_constraints<W>(J, f, sh, mrg)) { eps = 0; p = 0; m = 0; return; }
+    if (!(MANYC ? t_constraints_many<W>(J, f, sh, mrg) : t_constraints<W>(J, f, sh, mrg))) { eps = 0; p = 0; m = 0; return; }
     t_expsum<W>(J, f, eps, p, m);
     if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
 }

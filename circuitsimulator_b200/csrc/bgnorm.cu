@@ -37,10 +37,10 @@ using namespace bg;
 // ------------------------------------------------------------------------------------------
 // device-side records
 // ------------------------------------------------------------------------------------------
-// alive: 0 = annihilated by the projector; ROUTE_TPP = evaluated by k_pairs_tpp (one thread per
-// inner product); ROUTE_WARP = evaluated by k_pairs (one warp per inner product: any number of
-// parity checks).
-enum { ROUTE_DEAD = 0, ROUTE_TPP = 1, ROUTE_WARP = 2 };
+// alive: 0 = annihilated by the projector; ROUTE_TPP / ROUTE_TPP_MANY = evaluated by k_pairs_tpp (one
+// thread per inner product; _MANY: more than TPP_MAXC parity checks, pivot history in shared memory);
+// ROUTE_WARP = evaluated by k_pairs (one warp per inner product; only under BG_KERNEL=warp).
+enum { ROUTE_DEAD = 0, ROUTE_TPP = 1, ROUTE_WARP = 2, ROUTE_TPP_MANY = 3 };
 struct SampleRec {          // one projected theta in ambient form (see bg_device.cuh: ambient())
     int32_t alive, k1, npf, Q;
     uint64_t D1, D2, Cpend, Cbeta;
@@ -66,7 +66,7 @@ struct PrepArgs {
     // optional dump of the native state before projection (active-mask layout)
     bg_state* raw_out; uint64_t* raw_A;
     int force_warp;                     // route every sample to the warp-per-pair kernel
-    unsigned long long* n_warp_routed;  // device counter
+    unsigned long long* n_warp_routed;  // device counter: samples NOT taken by the plain k_pairs_tpp
 };
 
 struct PairArgs {
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
         Ambient<NS> am;
         make_ambient<NS>(st, am);
         if (lane == 0) {
-            const int route = (a.force_warp || popcw(am.Cpend) > TPP_MAXC) ? ROUTE_WARP : ROUTE_TPP;
-            if (route == ROUTE_WARP) atomicAdd(a.n_warp_routed, 1ull);
+            const int route = a.force_warp ? ROUTE_WARP : (popcw(am.Cpend) > TPP_MAXC ? ROUTE_TPP_MANY : ROUTE_TPP);
+            if (route != ROUTE_TPP) atomicAdd(a.n_warp_routed, 1ull);
             r->alive = route; r->k1 = am.k1; r->npf = npf; r->Q = (int32_t)am.f.Q;
             r->D1 = (uint64_t)am.f.D1; r->D2 = (uint64_t)am.f.D2;
             r->Cpend = (uint64_t)am.Cpend; r->Cbeta = (uint64_t)am.Cbeta;
@@ -263,15 +263,18 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
     return (long long)(((unsigned long long)hi << 32) | lo);
 }
 
-template <typename W, bool EXACT, bool TRI>
+template <typename W, bool EXACT, bool TRI, bool MANYC>
 __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     const int lane = bg_lane(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int t = a.t;
+    if (MANYC && *a.n_warp_routed == 0ull) return;      // nothing has more than TPP_MAXC parity checks
+    // per warp: t ambient rows (+ t check rows when MANYC); per thread: t working rows (+ t history rows)
+    const int amb_rows = MANYC ? 2 * t : t;
     uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
-    W* s_amb = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + warp * t;
-    W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * t + threadIdx.x;
+    W* s_amb = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + warp * amb_rows;
+    W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * amb_rows + threadIdx.x;
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
     Rows<W> rows; rows.base = s_rows; rows.stride = blockDim.x;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
         const int idx = (int)(item / (unsigned)a.chunks_per_sample);
         const int c = (int)(item % (unsigned)a.chunks_per_sample);
         const SampleRec* r = &a.recs[idx];
-        if (r->alive != ROUTE_TPP) continue;
+        if (r->alive != (MANYC ? ROUTE_TPP_MANY : ROUTE_TPP)) continue;
         const int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
         const int diag_index = TRI ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
@@ -295,8 +298,19 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
         for (int q = lane; q < t; q += 32) s_amb[q] = (W)r->J[q];
         TShared<W> sh;
         sh.J = s_amb; sh.D1 = (W)r->D1; sh.D2 = (W)r->D2; sh.Q = (uint32_t)r->Q; sh.k1 = r->k1; sh.t = t;
-        sh.ncons = 0; sh.cbeta = 0;
-        {
+        sh.ncons = 0; sh.cbeta = 0; sh.cwv = s_amb + t; sh.cbetav = 0;
+        if (MANYC) {                      // compact the check rows into shared memory, in row order
+            const uint64_t pend = r->Cpend, cbeta = r->Cbeta;
+            for (int q = lane; q < t; q += 32)
+                if ((pend >> q) & 1ull) s_amb[t + __popcll(pend & ((1ull << q) - 1ull))] = (W)r->Cw[q];
+            sh.ncons = __popcll(pend);
+            uint64_t cb = 0;
+            for (uint64_t rem = pend; rem; rem &= rem - 1) {
+                const int b = __ffsll((long long)rem) - 1;
+                cb |= ((cbeta >> b) & 1ull) << __popcll(pend & ((1ull << b) - 1ull));
+            }
+            sh.cbetav = (W)cb;
+        } else {
             const uint64_t cbeta = r->Cbeta;
 #pragma unroll
             for (int j = 0; j < TPP_MAXC; j++) sh.cw[j] = 0;
@@ -322,8 +336,8 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
             if (i < i1 && !(TRI && nat < diag_index)) {
                 const W term = (W)terms[i];
                 int e, p, m;
-                if (EXACT) t_term_H<W>(rows, sh, term, e, p, m);
-                else t_term_L<W>(rows, sh, term, e, p, m);
+                if (EXACT) t_term_H<W, MANYC>(rows, sh, term, e, p, m);
+                else t_term_L<W, MANYC>(rows, sh, term, e, p, m);
                 if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
                 else zw_add(z, e, p, m, sh_);
                 if (a.epm) {
@@ -785,17 +799,18 @@ template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const Pair
     return 0;
 }
 
-template <typename W, bool EXACT, bool TRI> static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
+template <typename W, bool EXACT, bool TRI, bool MANYC>
+static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
     if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pairs_tpp<W, EXACT, TRI><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
+        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pairs_tpp<W, EXACT, TRI, MANYC><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     return 0;
 }
-template <typename W> static int launch_tpp_w(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
-    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false>(ctx, a, blocks, smem);
-    return a.tri ? launch_tpp_inst<W, false, true>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false>(ctx, a, blocks, smem);
+template <typename W, bool MANYC> static int launch_tpp_w(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
+    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false, MANYC>(ctx, a, blocks, smem);
+    return a.tri ? launch_tpp_inst<W, false, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false, MANYC>(ctx, a, blocks, smem);
 }
 
 // Fill in chunking / staging and launch the pair kernels: k_pairs_tpp for the samples routed to it,
@@ -823,17 +838,22 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     a.terms = ctx->d_terms_sorted;
     a.term_nat = ctx->d_term_nat;
     if (!ctx->force_warp) {
-        a.counter = ctx->d_counters;
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;
         const int tw = ctx->tpp_warps;
-        const size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb;
         long long tb = (long long)ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK / tw;
         const long long tneed = (long long)((items + tw - 1) / tw);
         if (tb > tneed) tb = tneed;
         if (tb < 1) tb = 1;
-        if (a.t <= 32) { if (launch_tpp_w<uint32_t>(ctx, a, (int)tb, smem)) return 1; }
-        else { if (launch_tpp_w<uint64_t>(ctx, a, (int)tb, smem)) return 1; }
+        // samples with <= TPP_MAXC parity checks, then (returns at once if there are none) the rest
+        a.counter = ctx->d_counters;
+        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb;
+        if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
+        else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
+        a.counter = ctx->d_counters + 3;
+        smem = (size_t)a.smem_terms * 8 + 2 * ((size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb);
+        if (a.t <= 32) return launch_tpp_w<uint32_t, true>(ctx, a, (int)tb, smem);
+        return launch_tpp_w<uint64_t, true>(ctx, a, (int)tb, smem);
     }
     a.counter = ctx->d_counters + 3;
     a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;

@@ -72,19 +72,27 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
     Zw z; z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
     if (alive) {
         TShared<W> sh;
+        W cwv[64];
         sh.J = Jrows; sh.D1 = D1; sh.D2 = D2; sh.Q = Q; sh.k1 = k1; sh.t = t; sh.ncons = 0; sh.cbeta = 0;
+        sh.cwv = cwv; sh.cbetav = 0;
+        for (int j = 0; j < TPP_MAXC; j++) sh.cw[j] = 0;
         for (W r = Cpend; r; r &= r - 1) {
             int b = tlowest(r);
-            if (sh.ncons >= TPP_MAXC) return -1;           // routed to the warp-per-pair kernel on the device
-            sh.cw[sh.ncons] = Cwrows[b];
-            sh.cbeta |= (uint32_t)((Cbeta >> b) & 1) << sh.ncons;
+            cwv[sh.ncons] = Cwrows[b];
+            sh.cbetav |= (W)((Cbeta >> b) & 1) << sh.ncons;
+            if (sh.ncons < TPP_MAXC) { sh.cw[sh.ncons] = Cwrows[b]; sh.cbeta |= (uint32_t)((Cbeta >> b) & 1) << sh.ncons; }
             sh.ncons++;
         }
-        W work[64];
+        const bool many = sh.ncons > TPP_MAXC;      // the device routes these to the MANYC instantiation
+        W work[128];
         Rows<W> rows; rows.base = work; rows.stride = 1;
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
-            if (exact) t_term_H<W>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W>(rows, sh, (W)terms[i], e, p, m);
+            if (many) {
+                if (exact) t_term_H<W, true>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, true>(rows, sh, (W)terms[i], e, p, m);
+            } else {
+                if (exact) t_term_H<W, false>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, false>(rows, sh, (W)terms[i], e, p, m);
+            }
             g_bg_work.pairs++;
             zw_add(z, e, p, m, t / 2 + 1);
             if (epm) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m; }

@@ -107,3 +107,25 @@ def test_L_chi_loop_vs_compiled_reference_fixture(emu, oracle, name):
         assert got["alive"] == d["alive"][l]
         if d["alive"][l]:
             assert all(epm_equal(tuple(got["epm"][i]), tuple(d["epm"][l][i])) for i in range(len(terms)))
+
+
+def test_thread_per_pair_with_many_parity_checks(emu, oracle):
+    """Low-dimensional thetas (many parity checks): the pivot history moves from registers to the
+    thread's shared-memory rows (t_constraints_many)."""
+    rs = np.random.RandomState(3)
+    from oracle.oracle import Projector
+    for t in (12, 40):
+        L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(4)]
+        terms = [oracle.Lbits(i, L) for i in range(16)]
+        empty = Projector.make(t, [], [], [])
+        seen = set()
+        for j in range(30):
+            s = oracle.random_state_philox(t, 9, 0, j)
+            for _ in range((j * 3) % (t + 1)):
+                oracle.measure_pauli(s, 0, int(rs.randint(1, 2 ** 62)) & ((1 << t) - 1) or 1, 0)
+            seen.add(t - s.k)
+            got = emu.terms(s, empty, 0, False, t, terms, tpp=True)
+            assert got["alive"] == 1
+            for i in range(16):
+                assert epm_equal(tuple(got["epm"][i]), oracle.inner_product(s, oracle.prepL(i, t, L)))
+        assert max(seen) > 6
