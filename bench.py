@@ -32,6 +32,8 @@ CONFIGS = {
     # name: (stream file, samples per projector, forced k for |L>, description)
     "hidden_shift_n40_t40_k9_L65536": ("hs_t40_k9_bit0.txt", 65536, 9,
                                        "random hidden-shift n=40, t=40 T gates, |L> k=9 (chi=512), L=2^16"),
+    "hidden_shift_n40_t40_k9_L8192": ("hs_t40_k9_bit0.txt", 8192, 9,
+                                      "config 4 at 1/8 of the samples (what one of 8 GPUs sees)"),
     "hidden_shift_n40_t16_L16384": ("hs_t16_bit6.txt", 16384, 0,
                                     "random hidden-shift n=40, t=16 T gates, exact |H^t> (chi=256), L=2^14"),
     "htstack_t4_L1024": ("htstack_t4.txt", 1024, 0, "HTstack.circ output 0, t=4 (chi=4), L=1024"),

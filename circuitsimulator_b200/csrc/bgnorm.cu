@@ -65,6 +65,7 @@ struct PrepArgs {
     const uint64_t* terms; int exact;
     // optional dump of the native state before projection (active-mask layout)
     bg_state* raw_out; uint64_t* raw_A;
+    long long* zw; long long* zw2;      // per-sample accumulators, zeroed here (zw2 may be null)
     int force_warp;                     // route every sample to the warp-per-pair kernel
     unsigned long long* n_warp_routed;  // device counter: samples NOT taken by the plain k_pairs_tpp
 };
@@ -135,6 +136,10 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
         bool alive = true;
         if (a.project) alive = project_native<NS>(st, a.P, npf);
         SampleRec* r = &a.recs[idx];
+        if (lane < 4) {
+            if (a.zw) a.zw[(size_t)idx * 4 + lane] = 0;
+            if (a.zw2) a.zw2[(size_t)idx * 4 + lane] = 0;
+        }
         if (!alive) {
             if (lane == 0) { r->alive = 0; r->k1 = 0; r->npf = 0; r->Q = 0; }
             continue;
@@ -422,6 +427,32 @@ __global__ void k_finalize_sampled(const SampleRec* recs, const long long* zw, i
     per_sample[i] = v;
 }
 
+// finalize + fixed-order sum in one single-CTA launch (the same summation order as k_sum over the
+// per-sample values: thread-strided partials, then a binary tree)
+__global__ void __launch_bounds__(1024) k_finalize_sum_sampled(const SampleRec* recs, const long long* zw, int n, int t,
+                                                               double* per_sample, double* out) {
+    __shared__ double sh[1024];
+    const int shf = t / 2 + 1;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        double v = 0.0;
+        if (recs[i].alive) {
+            double re, im;
+            zw_to_complex(&zw[(size_t)i * 4], re, im);
+            v = ldexp(re * re + im * im, t - recs[i].npf - 2 * shf);
+        }
+        per_sample[i] = v;
+        acc += v;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
 // exact mode: part_i = pf_i * (diag_i) if i == j, plus (2 pf_i Re(offdiag_i), 0)   (innerprod.c:254-260)
 __global__ void k_finalize_exact(const SampleRec* recs, const long long* zw, const long long* zw2, int n, int t,
                                  double* per_re, double* per_im) {
@@ -494,7 +525,7 @@ struct bg_ctx {
     long long* d_zw2 = nullptr; size_t zw2_cap = 0;
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
-    int ctas_per_sm = 8, items_factor = 8;
+    int ctas_per_sm = 8, items_factor = 32;
     int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
@@ -920,20 +951,19 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
     pa.seed = ctx->seed; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
     pa.cdf = ctx->d_cdf;
+    pa.zw = ctx->d_zw;
     CK(cudaEventRecord(ctx->evp0, ctx->stream));
     if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
     CK(cudaEventRecord(ctx->evp1, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
     PairArgs qa; memset(&qa, 0, sizeof qa);
     qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
     qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
     if (launch_pairs(ctx, qa)) return 1;
     CK(cudaEventRecord(ctx->evp2, ctx->stream));
     ctx->phase_events = true;
-    k_finalize_sampled<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per);
-    k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red + red_slot);
+    k_finalize_sum_sampled<<<1, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, ctx->d_red + red_slot);
     CK(cudaGetLastError());
-    ctx->stats.launches += 2;
+    ctx->stats.launches += 1;
     return 0;
 }
 
@@ -1051,9 +1081,8 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
         pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
         pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
         pa.terms = ctx->d_terms; pa.exact = ctx->exact;
+        pa.zw = ctx->d_zw; pa.zw2 = ctx->d_zw2;
         if (launch_prepare(ctx, SRC_TERMS, pa)) return 1;
-        CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_zw2, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
         PairArgs qa; memset(&qa, 0, sizeof qa);
         qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)chi;
         qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2; qa.tri = 1;
@@ -1147,8 +1176,8 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     PrepArgs pa; memset(&pa, 0, sizeof pa);
     pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = project ? 1 : 0; pa.P = ctx->d_P;
     pa.states = dth;
+    pa.zw = ctx->d_zw;
     if (launch_prepare(ctx, SRC_STATES, pa)) return 1;
-    CK(cudaMemsetAsync(ctx->d_zw, 0, (size_t)n * 4 * sizeof(long long), ctx->stream));
     PairArgs qa; memset(&qa, 0, sizeof qa);
     qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)chi;
     qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2; qa.epm = depm;
