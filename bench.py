@@ -295,36 +295,35 @@ def main():
     G = bg.Projector.make(*Gd)
     H = bg.Projector.make(*Hd)
 
-    # two contexts on this GPU (one per projector) so both stay resident for the device-timed loop
-    ctxs = [bg.Backend(local), bg.Backend(local)]
-    tstream = torch.cuda.current_stream()
+    # one context per GPU; both projectors of a probability() evaluation form one prepared job.
+    # Work runs on a non-default torch stream (a CUDA graph cannot be captured on the legacy stream).
+    ctx = bg.Backend(local)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
     if world > 1:
-        uid = [ctxs[0].nccl_unique_id() if rank == 0 else None, ctxs[1].nccl_unique_id() if rank == 0 else None]
+        uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-    for j, c in enumerate(ctxs):
-        c.set_stream(tstream.cuda_stream)
-        c.set_shard(rank, world)
-        if world > 1:
-            c.nccl_join(uid[j])
-        c.set_decomposition(t, exact, L)
-    lop3_peak, popc_peak = ctxs[0].measure_int_peak()
+    ctx.set_stream(tstream.cuda_stream)
+    ctx.set_shard(rank, world)
+    if world > 1:
+        ctx.nccl_join(uid[0])
+    ctx.set_decomposition(t, exact, L)
+    lop3_peak, popc_peak = ctx.measure_int_peak()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: projector + decomposition uploaded once, kernels only in the loop
-    ctxs[0].sampled_prepare(G, samples, 1, 1001)
-    ctxs[1].sampled_prepare(H, samples, 1, 1002)
+    # ---- device-resident arm: projectors + decomposition uploaded once; the step replays one CUDA graph
+    # (theta draw + projection, L x chi loop, reduction for G' then H'), then one NCCL all-reduce of the
+    # partial sums and a 16-byte read-back.
+    ctx.sampled_prepare2(G, H, samples, 1, 1001, 1002)
     results = []
 
     def step_resident():
-        ctxs[0].sampled_run()
-        ctxs[1].sampled_run()
-        num = ctxs[0].sampled_finish(1.0)         # includes the NCCL all-reduce + 8-byte D2H
-        den = ctxs[1].sampled_finish(1.0)
-        results.append((num, den))
+        ctx.sampled_run()
+        results.append(ctx.sampled_finish2(1.0))
 
     sampler = ClockSampler(local)
     sampler.start()                      # samples through warm-up + timed region (all under the same load)
@@ -336,12 +335,11 @@ def main():
     e0.record(tstream)
     for _ in range(args.steps):
         step_resident()
-        for c in ctxs:
-            st = c.stats()
-            kernel_ms += st["kernel_ms"]
-            prepare_ms += st["prepare_ms"]
-            pairs_ms += st["pairs_ms"]
-            launches += st["launches"]
+        st = ctx.stats()
+        kernel_ms += st["kernel_ms"]
+        prepare_ms += st["prepare_ms"]
+        pairs_ms += st["pairs_ms"]
+        launches += st["launches"]
     e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -361,9 +359,8 @@ def main():
     # ---- end-to-end arm: the C-ABI calls a host makes per probability(): decomposition + projector
     # from HOST memory, kernels, all-reduce, result back to the host — every step.
     def step_e2e():
-        for c, P, seed in ((ctxs[0], G, 2001), (ctxs[1], H, 2002)):
-            c.set_decomposition(t, exact, L)
-            c.sampled_norm(P, samples, 1, seed, 1.0)
+        ctx.set_decomposition(t, exact, L)
+        ctx.sampled_norm2(G, H, samples, 1, 2001, 2002, 1.0)
 
     for _ in range(2):
         step_e2e()
@@ -380,7 +377,7 @@ def main():
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = pairs_per_step * args.steps / float(tw.item())
     import ctypes
-    h2d = 2 * (chi * 8 + ctypes.sizeof(bg.Projector))      # terms table + bg_projector, per projector
+    h2d = 2 * chi * 8 + chi * 4 + 2 * ctypes.sizeof(bg.Projector)   # term tables (natural, sorted, index) + 2 bg_projector
     d2h = 2 * 8
 
     if rank == 0:
@@ -429,8 +426,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(cfgname)
         print(json.dumps(line))
-    for c in ctxs:
-        c.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -93,6 +93,9 @@ def load_library():
         "bg_sampled_prepare": [vp, _P(Projector), u64, i32, u64],
         "bg_sampled_run": [vp],
         "bg_sampled_finish": [vp, dbl, _P(dbl)],
+        "bg_sampled_norm2": [vp, _P(Projector), _P(Projector), u64, i32, u64, u64, dbl, _P(dbl)],
+        "bg_sampled_prepare2": [vp, _P(Projector), _P(Projector), u64, i32, u64, u64],
+        "bg_sampled_finish2": [vp, dbl, _P(dbl)],
         "bg_set_stream": [vp, vp],
         "bg_measure_int_peak": [vp, _P(dbl), _P(dbl)],
     }
@@ -114,7 +117,8 @@ def exported_symbols():
             "bg_set_decomposition", "bg_set_decomposition_bitmatrix", "bg_projector_from_bitmatrix",
             "bg_sampled_norm", "bg_exact_norm", "bg_inner_products", "bg_sampled_norm_from_states",
             "bg_measure_pauli", "bg_random_states", "bg_decomposition_terms", "bg_get_stats",
-            "bg_sampled_prepare", "bg_sampled_run", "bg_sampled_finish", "bg_set_stream", "bg_measure_int_peak"]
+            "bg_sampled_prepare", "bg_sampled_run", "bg_sampled_finish", "bg_sampled_norm2", "bg_sampled_prepare2",
+            "bg_sampled_finish2", "bg_set_stream", "bg_measure_int_peak"]
 
 
 def _states_arg(arr):
@@ -189,6 +193,19 @@ class Backend:
         out = C.c_double()
         self._ck(self.lib.bg_sampled_finish(self.ctx, norm, C.byref(out)))
         return out.value
+
+    def sampled_norm2(self, G, H, samples, bins=1, seed_g=0, seed_h=1, norm=1.0):
+        out = (C.c_double * 2)()
+        self._ck(self.lib.bg_sampled_norm2(self.ctx, C.byref(G), C.byref(H), samples, bins, seed_g, seed_h, norm, out))
+        return out[0], out[1]
+
+    def sampled_prepare2(self, G, H, samples, bins=1, seed_g=0, seed_h=1):
+        self._ck(self.lib.bg_sampled_prepare2(self.ctx, C.byref(G), C.byref(H), samples, bins, seed_g, seed_h))
+
+    def sampled_finish2(self, norm=1.0):
+        out = (C.c_double * 2)()
+        self._ck(self.lib.bg_sampled_finish2(self.ctx, norm, out))
+        return out[0], out[1]
 
     # -- parity / debug
     def inner_products(self, a, b):

@@ -506,7 +506,8 @@ struct bg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr, evp2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evp[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // per projector: before prepare, after prepare, after pairs
     int sm_count = 0;
     int rank = 0, world = 1;
     bool allreduce = true;
@@ -532,10 +533,15 @@ struct bg_ctx {
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
     double* d_red = nullptr;                    // [8] reduction outputs
     // prepared sampled run
-    bg_projector P_host;
-    uint64_t samples = 0; int bins = 1; uint64_t seed = 0;
+    int nproj = 1;                  // projectors of the prepared job (2: numerator and denominator together)
+    uint64_t samples = 0; int bins = 1; uint64_t seeds[2] = {0, 0};
     bool prepared = false;
     bool phase_events = false;
+    int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
+    // the prepared job replayed as one CUDA graph (BG_GRAPH=0 disables)
+    bool use_graph = true, capturing = false;
+    cudaGraphExec_t gexec = nullptr;
+    double* h_out = nullptr;        // pinned: 8 sums + 8 counters
     std::vector<double> bin_sums;
     bg_stats stats;
     std::string err;
@@ -550,7 +556,15 @@ static int fail(bg_ctx* ctx, const char* fmt, ...) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+static cudaError_t rec_event(bg_ctx* ctx, cudaEvent_t ev) {
+    return ctx->capturing ? cudaEventRecordWithFlags(ev, ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ev, ctx->stream);
+}
+static void drop_graph(bg_ctx* ctx) {
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+}
+
 template <typename T> static int ensure(bg_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (!(*cap >= need && *p)) drop_graph(ctx);        // a captured graph holds the old pointers
     if (*cap >= need && *p) return 0;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
@@ -588,15 +602,19 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaStreamCreate failed"); }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-    cudaEventCreate(&ctx->evp0); cudaEventCreate(&ctx->evp1); cudaEventCreate(&ctx->evp2);
-    if (cudaMalloc((void**)&ctx->d_P, sizeof(bg_projector)) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) cudaEventCreate(&ctx->evp[a][b]);
+    if (cudaMalloc((void**)&ctx->d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_out, 16 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 8 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cdf, (BG_MAX_T + 1) * sizeof(double)) != cudaSuccess) {
         int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
+    cudaMemset(ctx->d_red, 0, 8 * sizeof(double));
+    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
@@ -612,7 +630,9 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->evp0) { cudaEventDestroy(ctx->evp0); cudaEventDestroy(ctx->evp1); cudaEventDestroy(ctx->evp2); }
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) if (ctx->evp[a][b]) cudaEventDestroy(ctx->evp[a][b]);
+    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -621,6 +641,7 @@ extern "C" int bg_set_shard(bg_ctx* ctx, int rank, int world) {
     if (!ctx) return fail(nullptr, "bg_set_shard: null ctx");
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "bg_set_shard: bad rank %d of %d", rank, world);
     ctx->rank = rank; ctx->world = world;
+    drop_graph(ctx);
     return 0;
 }
 
@@ -630,6 +651,7 @@ extern "C" int bg_set_stream(bg_ctx* ctx, void* stream) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
     ctx->stream = (cudaStream_t)stream;
+    drop_graph(ctx);
     return 0;
 }
 
@@ -765,6 +787,7 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->prepared = false;
+    drop_graph(ctx);
     return 0;
 }
 
@@ -815,9 +838,9 @@ template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepA
 }
 static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
     a.force_warp = ctx->force_warp;
-    a.n_warp_routed = ctx->d_counters + 2;
+    a.n_warp_routed = ctx->d_counters + 4 * ctx->cur + 2;
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
 
@@ -864,8 +887,9 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     const long long need = (long long)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    a.pair_count = ctx->d_counters + 1;
-    a.n_warp_routed = ctx->d_counters + 2;
+    unsigned long long* cnt = ctx->d_counters + 4 * ctx->cur;
+    a.pair_count = cnt + 1;
+    a.n_warp_routed = cnt + 2;
     a.terms = ctx->d_terms_sorted;
     a.term_nat = ctx->d_term_nat;
     if (!ctx->force_warp) {
@@ -877,16 +901,16 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         if (tb > tneed) tb = tneed;
         if (tb < 1) tb = 1;
         // samples with <= TPP_MAXC parity checks, then (returns at once if there are none) the rest
-        a.counter = ctx->d_counters;
+        a.counter = cnt;
         size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb;
         if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
         else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
-        a.counter = ctx->d_counters + 3;
+        a.counter = cnt + 3;
         smem = (size_t)a.smem_terms * 8 + 2 * ((size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb);
         if (a.t <= 32) return launch_tpp_w<uint32_t, true>(ctx, a, (int)tb, smem);
         return launch_tpp_w<uint64_t, true>(ctx, a, (int)tb, smem);
     }
-    a.counter = ctx->d_counters + 3;
+    a.counter = cnt + 3;
     a.smem_terms = padded <= SMEM_TERMS_MAX ? (int)padded : 0;
     const size_t smem = (size_t)a.smem_terms * 8;
     if (a.t <= 32) return ctx->exact ? launch_pairs_ns<1, true>(ctx, a, (int)blocks, smem) : launch_pairs_ns<1, false>(ctx, a, (int)blocks, smem);
@@ -923,47 +947,77 @@ static double clifford_closed_form(const bg_projector* P) {
     return sum / (1 + (double)P->nstabs);
 }
 
-extern "C" int bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed) {
+static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* Ps, uint64_t samples, int bins,
+                             const uint64_t* seeds) {
     if (!ctx) return fail(nullptr, "bg_sampled_prepare: null ctx");
     if (ctx->t <= 0) return fail(ctx, "bg_sampled_prepare: call bg_set_decomposition first");
-    if (check_projector(ctx, P)) return 1;
-    if (P->nstabs == 0) return fail(ctx, "bg_sampled_prepare: empty projector (use bg_sampled_norm for the closed form)");
+    for (int j = 0; j < nproj; j++) {
+        if (check_projector(ctx, Ps[j])) return 1;
+        if (Ps[j]->nstabs == 0) return fail(ctx, "bg_sampled_prepare: empty projector (use bg_sampled_norm for the closed form)");
+    }
     if (bins < 1) return fail(ctx, "bg_sampled_prepare: bins = %d", bins);
     if (samples < 1) return fail(ctx, "bg_sampled_prepare: samples = 0");
     CK(cudaSetDevice(ctx->device));
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
     if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
-    ctx->P_host = *P;
-    CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes = sizeof(bg_projector);
-    ctx->samples = samples; ctx->bins = bins; ctx->seed = seed;
+    for (int j = 0; j < nproj; j++)
+        CK(cudaMemcpyAsync(ctx->d_P + j, Ps[j], sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // the caller's projector may be a temporary
+    ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
+    ctx->nproj = nproj; ctx->samples = samples; ctx->bins = bins;
+    for (int j = 0; j < nproj; j++) ctx->seeds[j] = seeds[j];
     ctx->prepared = true;
+    drop_graph(ctx);
     return 0;
 }
 
-// one bin: prepare + pairs + finalize + sum into d_red[slot], d_red[4+slot] untouched
+extern "C" int bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed) {
+    return sampled_prepare_n(ctx, 1, &P, samples, bins, &seed);
+}
+
+extern "C" int bg_sampled_prepare2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
+                                   uint64_t seed_g, uint64_t seed_h) {
+    const bg_projector* Ps[2] = {G, H};
+    const uint64_t seeds[2] = {seed_g, seed_h};
+    return sampled_prepare_n(ctx, 2, Ps, samples, bins, seeds);
+}
+
+// one bin of projector ctx->cur: prepare + pairs + finalize/sum into d_red[red_slot]
 static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     const uint64_t mine = shard_count(ctx->samples, ctx->rank, ctx->world);
     const int n = (int)mine;
+    const int pj = ctx->cur;
     if (n == 0) { CK(cudaMemsetAsync(ctx->d_red + red_slot, 0, sizeof(double), ctx->stream)); return 0; }
     PrepArgs pa; memset(&pa, 0, sizeof pa);
-    pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P;
-    pa.seed = ctx->seed; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
+    pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P + pj;
+    pa.seed = ctx->seeds[pj]; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
     pa.cdf = ctx->d_cdf;
     pa.zw = ctx->d_zw;
-    CK(cudaEventRecord(ctx->evp0, ctx->stream));
+    CK(rec_event(ctx, ctx->evp[pj][0]));
     if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
-    CK(cudaEventRecord(ctx->evp1, ctx->stream));
+    CK(rec_event(ctx, ctx->evp[pj][1]));
     PairArgs qa; memset(&qa, 0, sizeof qa);
     qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
     qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
     if (launch_pairs(ctx, qa)) return 1;
-    CK(cudaEventRecord(ctx->evp2, ctx->stream));
+    CK(rec_event(ctx, ctx->evp[pj][2]));
     ctx->phase_events = true;
     k_finalize_sum_sampled<<<1, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, ctx->d_red + red_slot);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
+    return 0;
+}
+
+// enqueue the whole prepared job (all projectors, all bins) on ctx's stream
+static int enqueue_job(bg_ctx* ctx) {
+    CK(rec_event(ctx, ctx->ev0));
+    for (int pj = 0; pj < ctx->nproj; pj++) {
+        ctx->cur = pj;
+        for (int b = 0; b < ctx->bins; b++) if (run_bin(ctx, b, 4 * pj + b)) { ctx->cur = 0; return 1; }
+    }
+    ctx->cur = 0;
+    CK(rec_event(ctx, ctx->ev1));
     return 0;
 }
 
@@ -972,10 +1026,24 @@ extern "C" int bg_sampled_run(bg_ctx* ctx) {
     if (!ctx->prepared) return fail(ctx, "bg_sampled_run: bg_sampled_prepare not called");
     CK(cudaSetDevice(ctx->device));
     if (ctx->bins > 4) return fail(ctx, "bg_sampled_run: split-phase API supports at most 4 bins (use bg_sampled_norm)");
-    ctx->stats.launches = 0;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int b = 0; b < ctx->bins; b++) if (run_bin(ctx, b, b)) return 1;
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!ctx->use_graph) { ctx->stats.launches = 0; return enqueue_job(ctx); }
+    if (!ctx->gexec) {
+        // first run of this job: capture the launch sequence once, replay it afterwards
+        ctx->stats.launches = 0;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        ctx->capturing = true;
+        const int rc = enqueue_job(ctx);
+        ctx->capturing = false;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+        if (e != cudaSuccess) return fail(ctx, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&ctx->gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { ctx->gexec = nullptr; return fail(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    }
+    CK(cudaGraphLaunch(ctx->gexec, ctx->stream));
+    ctx->phase_events = true;
     return 0;
 }
 
@@ -990,40 +1058,58 @@ static double median_like_reference(std::vector<double>& v) {
     return (v[bins / 2] + v[bins / 2 - 1]) / 2;
 }
 
-static int collect_stats(bg_ctx* ctx) {
+// after the stream has been synchronised: event times and the pair counters (h_out[8..16))
+static int collect_stats(bg_ctx* ctx, int nproj, bool counters_in_h_out) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms = ms;
     ctx->stats.prepare_ms = ctx->stats.pairs_ms = 0;
     if (ctx->phase_events) {
-        float a = 0, b = 0;
-        if (cudaEventElapsedTime(&a, ctx->evp0, ctx->evp1) == cudaSuccess) ctx->stats.prepare_ms = a;
-        if (cudaEventElapsedTime(&b, ctx->evp1, ctx->evp2) == cudaSuccess) ctx->stats.pairs_ms = b;
+        for (int pj = 0; pj < nproj; pj++) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, ctx->evp[pj][0], ctx->evp[pj][1]) == cudaSuccess) ctx->stats.prepare_ms += a;
+            if (cudaEventElapsedTime(&b, ctx->evp[pj][1], ctx->evp[pj][2]) == cudaSuccess) ctx->stats.pairs_ms += b;
+        }
         ctx->phase_events = false;
     }
-    unsigned long long c[2];
-    CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
-    ctx->stats.pairs = c[1];
+    unsigned long long c[8];
+    if (counters_in_h_out) memcpy(c, ctx->h_out + 8, sizeof c);
+    else CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.pairs = 0;
+    for (int pj = 0; pj < nproj; pj++) ctx->stats.pairs += c[4 * pj + 1];
+    return 0;
+}
+
+static int sampled_finish_n(bg_ctx* ctx, double* out) {
+    if (!ctx) return fail(nullptr, "bg_sampled_finish: null ctx");
+    if (!ctx->prepared) return fail(ctx, "bg_sampled_finish: nothing was run");
+    if (!out) return fail(ctx, "bg_sampled_finish: null out");
+    CK(cudaSetDevice(ctx->device));
+    if (allreduce_red(ctx, 8)) return 1;                      // one all-reduce for every projector and bin
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_red, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out + 8, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes = (uint64_t)ctx->nproj * ctx->bins * sizeof(double);
+    if (ctx->gexec) ctx->stats.launches = (uint64_t)ctx->nproj * ctx->bins * 4;   // prepare, 2 x pairs, finalize per bin
+    if (collect_stats(ctx, ctx->nproj, true)) return 1;
+    for (int pj = 0; pj < ctx->nproj; pj++) {
+        std::vector<double> v(ctx->bins);
+        for (int b = 0; b < ctx->bins; b++) v[b] = ctx->h_out[4 * pj + b] / (double)ctx->samples;   // total/samples (innerprod.c:83)
+        out[pj] = median_like_reference(v);
+    }
     return 0;
 }
 
 extern "C" int bg_sampled_finish(bg_ctx* ctx, double norm, double* out) {
     (void)norm;
-    if (!ctx) return fail(nullptr, "bg_sampled_finish: null ctx");
-    if (!ctx->prepared) return fail(ctx, "bg_sampled_finish: nothing was run");
-    if (!out) return fail(ctx, "bg_sampled_finish: null out");
-    CK(cudaSetDevice(ctx->device));
-    if (allreduce_red(ctx, ctx->bins)) return 1;
-    double sums[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(sums, ctx->d_red, ctx->bins * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes = ctx->bins * sizeof(double);
-    if (collect_stats(ctx)) return 1;
-    ctx->stats.pairs *= 1;       // pairs of the LAST bin only are in the counter; fine for bins == 1
-    std::vector<double> v(ctx->bins);
-    for (int b = 0; b < ctx->bins; b++) v[b] = sums[b] / (double)ctx->samples;     // total/samples (innerprod.c:83)
-    *out = median_like_reference(v);
-    return 0;
+    if (ctx && ctx->nproj != 1) return fail(ctx, "bg_sampled_finish: the prepared job has 2 projectors (use bg_sampled_finish2)");
+    return sampled_finish_n(ctx, out);
+}
+
+extern "C" int bg_sampled_finish2(bg_ctx* ctx, double norm, double out[2]) {
+    (void)norm;
+    if (ctx && ctx->nproj != 2) return fail(ctx, "bg_sampled_finish2: the prepared job has 1 projector");
+    return sampled_finish_n(ctx, out);
 }
 
 extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed,
@@ -1036,24 +1122,44 @@ extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samp
     if (bins < 1) return fail(ctx, "bg_sampled_norm: bins = %d", bins);
     if (bg_sampled_prepare(ctx, P, samples, 1, seed)) return 1;
     std::vector<double> v(bins);
-    double total_ms = 0; uint64_t total_pairs = 0, launches = 0;
+    double total_ms = 0, prep_ms = 0, pair_ms = 0; uint64_t total_pairs = 0, launches = 0;
+    ctx->cur = 0;
     for (int b = 0; b < bins; b++) {
         ctx->stats.launches = 0;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         if (run_bin(ctx, b, 0)) return 1;
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         if (allreduce_red(ctx, 1)) return 1;
-        double s = 0;
-        CK(cudaMemcpyAsync(&s, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_out, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_out + 8, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (collect_stats(ctx)) return 1;
+        if (collect_stats(ctx, 1, true)) return 1;
         total_ms += ctx->stats.kernel_ms; total_pairs += ctx->stats.pairs; launches += ctx->stats.launches;
-        v[b] = s / (double)samples;
+        prep_ms += ctx->stats.prepare_ms; pair_ms += ctx->stats.pairs_ms;
+        v[b] = ctx->h_out[0] / (double)samples;
     }
     ctx->stats.kernel_ms = total_ms; ctx->stats.pairs = total_pairs; ctx->stats.launches = launches;
+    ctx->stats.prepare_ms = prep_ms; ctx->stats.pairs_ms = pair_ms;
     ctx->stats.d2h_bytes = bins * sizeof(double);
     *out = median_like_reference(v);
     return 0;
+}
+
+// Numerator and denominator of one probability() evaluation (probability.c:197-198): both
+// projectors against the same decomposition, ONE all-reduce and one host synchronisation.
+extern "C" int bg_sampled_norm2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
+                                uint64_t seed_g, uint64_t seed_h, double norm, double out[2]) {
+    if (!ctx) return fail(nullptr, "bg_sampled_norm2: null ctx");
+    if (!out || !G || !H) return fail(ctx, "bg_sampled_norm2: null argument");
+    const bool plain = G->nstabs > 0 && H->nstabs > 0 && G->nqubits > 0 && H->nqubits > 0 && bins >= 1 && bins <= 4;
+    if (!plain) {            // closed forms / many bins: one projector at a time
+        if (bg_sampled_norm(ctx, G, samples, bins, seed_g, norm, &out[0])) return 1;
+        return bg_sampled_norm(ctx, H, samples, bins, seed_h, norm, &out[1]);
+    }
+    if (bg_sampled_prepare2(ctx, G, H, samples, bins, seed_g, seed_h)) return 1;
+    ctx->stats.launches = 0;
+    if (enqueue_job(ctx)) return 1;
+    return sampled_finish_n(ctx, out);
 }
 
 // ---- exact norm ---------------------------------------------------------------------------
@@ -1100,7 +1206,7 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
     CK(cudaMemcpyAsync(s, ctx->d_red, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes = sizeof s;
-    if (collect_stats(ctx)) return 1;
+    if (collect_stats(ctx, 1, false)) return 1;
     *out = sqrt(s[0] * s[0] + s[1] * s[1]);                                 // ComplexMag (innerprod.c:198)
     return 0;
 }
@@ -1192,7 +1298,7 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     if (per_sample) CK(cudaMemcpyAsync(per_sample, ctx->d_per, n_states * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (epm) CK(cudaMemcpyAsync(epm, depm, n_states * chi * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (collect_stats(ctx)) return 1;
+    if (collect_stats(ctx, 1, false)) return 1;
     ctx->stats.h2d_bytes = n_states * sizeof(bg_state);
     ctx->stats.d2h_bytes = sizeof(double) + (per_sample ? n_states * sizeof(double) : 0) + (epm ? n_states * chi * 12 : 0);
     if (mean) *mean = s / (double)n_states;

@@ -170,8 +170,18 @@ int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
  * resident: upload (projector, decomposition) once, then run the kernel only.
  * bg_sampled_norm == bg_sampled_prepare + bg_sampled_run + bg_sampled_finish. */
 int  bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed);
-int  bg_sampled_run(bg_ctx* ctx);                       /* async on ctx's stream          */
-int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* sync, reduce, all-reduce */
+int  bg_sampled_run(bg_ctx* ctx);                       /* async on ctx's stream; the launch sequence is
+                                                           captured once into a CUDA graph and replayed */
+int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* all-reduce, D2H, sync         */
+
+/* Numerator and denominator of one probability() evaluation together — both projectors against the
+ * same decomposition (libcirc/probability.c:197-198) — with ONE all-reduce and one host sync.
+ * out[0] = G', out[1] = H'.  bg_sampled_norm2 = bg_sampled_prepare2 + run + bg_sampled_finish2. */
+int  bg_sampled_norm2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
+                      uint64_t seed_g, uint64_t seed_h, double norm, double out[2]);
+int  bg_sampled_prepare2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
+                         uint64_t seed_g, uint64_t seed_h);
+int  bg_sampled_finish2(bg_ctx* ctx, double norm, double out[2]);
 
 /* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
  * instead of the context's own, so that the caller's events bracket the kernels. */

@@ -364,3 +364,29 @@ def test_bins_median_of_means(be, oracle):
     # other compare equal, so which of them qsort leaves in the middle is libc's business — the result is
     # one of the bin means, bit for bit what the reference's qsort call would pick from the same values
     assert min(abs(got - m) for m in means) < 1e-12
+
+
+def test_two_projector_job_and_graph_replay(be):
+    """bg_sampled_norm2 / prepare2+run+finish2 (one CUDA-graph replay, one all-reduce) give exactly the
+    numbers of two separate bg_sampled_norm calls, on every replay."""
+    import circuitsimulator_b200 as bg
+    import torch
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
+    be.set_decomposition(cfg["t"], True)
+    g, h = to_bg(G), to_bg(H)
+    a = be.sampled_norm(g, 3000, 1, 31, 1.0)
+    b = be.sampled_norm(h, 3000, 1, 32, 1.0)
+    assert be.sampled_norm2(g, h, 3000, 1, 31, 32, 1.0) == (a, b)
+    be.sampled_prepare2(g, h, 3000, 2, 31, 32)
+    first = None
+    for _ in range(3):
+        be.sampled_run()
+        out = be.sampled_finish2(1.0)
+        first = first or out
+        assert out == first
+    st = be.stats()
+    assert st["launches"] > 0 and st["pairs"] > 0
+    # bins = 1 job equals the plain calls
+    be.sampled_prepare2(g, h, 3000, 1, 31, 32)
+    be.sampled_run()
+    assert be.sampled_finish2(1.0) == (a, b)
