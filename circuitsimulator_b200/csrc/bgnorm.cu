@@ -78,7 +78,10 @@ struct PairArgs {
     const int32_t* term_nat; // natural index i of sorted position (epm output, pair ordering of the exact norm)
     int nterms;
     int t;
-    int chunk, chunks_per_sample;
+    // work items: first n_samples * chunks_per_sample big items (terms [c*chunk, (c+1)*chunk) below tail_start),
+    // then n_samples * tail_chunks small ones of 32 terms each covering [tail_start, nterms) — big items
+    // first, small ones last, so that the last wave is short (the counter hands them out in this order)
+    int chunk, chunks_per_sample, tail_start, tail_chunks;
     unsigned long long* counter;
     long long* zw;          // [n_samples][4]
     long long* zw2;         // [n_samples][4]   (exact-norm mode: off-diagonal part)
@@ -89,6 +92,21 @@ struct PairArgs {
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
 };
+
+// work item -> (sample index, term range)
+__device__ __forceinline__ void item_range(const PairArgs& a, unsigned long long item, int& idx, int& i0, int& i1) {
+    const unsigned long long nbig = (unsigned long long)a.n_samples * (unsigned)a.chunks_per_sample;
+    if (item < nbig) {
+        idx = (int)(item / (unsigned)a.chunks_per_sample);
+        const int c = (int)(item % (unsigned)a.chunks_per_sample);
+        i0 = c * a.chunk; i1 = min(a.tail_start, i0 + a.chunk);
+    } else {
+        const unsigned long long j = item - nbig;
+        idx = (int)(j / (unsigned)a.tail_chunks);
+        const int c = (int)(j % (unsigned)a.tail_chunks);
+        i0 = a.tail_start + 32 * c; i1 = min(a.nterms, i0 + 32);
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // k_prepare
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
 
-    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)a.chunks_per_sample;
+    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
     const int sh = a.t / 2 + 1;
     unsigned long long my_pairs = 0;
     while (true) {
@@ -212,11 +230,10 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
         if (lane == 0) item = atomicAdd(a.counter, 1ull);
         item = __shfl_sync(BG_FULL, item, 0);
         if (item >= n_items) break;
-        const int idx = (int)(item / (unsigned)a.chunks_per_sample);
-        const int c = (int)(item % (unsigned)a.chunks_per_sample);
+        int idx, i0, i1;
+        item_range(a, item, idx, i0, i1);
         const SampleRec* r = &a.recs[idx];
         if (r->alive != ROUTE_WARP) continue;
-        const int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
         // exactProjectorWork: sample i meets the terms j >= i (natural indices)
         const int diag_index = a.tri ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
     Rows<W> rows; rows.base = s_rows; rows.stride = blockDim.x;
 
-    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)a.chunks_per_sample;
+    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
     const int sh_ = t / 2 + 1;
     unsigned long long my_pairs = 0;
     while (true) {
@@ -292,11 +309,10 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
         if (lane == 0) item = atomicAdd(a.counter, 1ull);
         item = __shfl_sync(BG_FULL, item, 0);
         if (item >= n_items) break;
-        const int idx = (int)(item / (unsigned)a.chunks_per_sample);
-        const int c = (int)(item % (unsigned)a.chunks_per_sample);
+        int idx, i0, i1;
+        item_range(a, item, idx, i0, i1);
         const SampleRec* r = &a.recs[idx];
         if (r->alive != (MANYC ? ROUTE_TPP_MANY : ROUTE_TPP)) continue;
-        const int i0 = c * a.chunk, i1 = min(a.nterms, i0 + a.chunk);
         const int diag_index = TRI ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
         __syncwarp();
@@ -526,7 +542,7 @@ struct bg_ctx {
     long long* d_zw2 = nullptr; size_t zw2_cap = 0;
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
-    int ctas_per_sm = 8, items_factor = 32;
+    int ctas_per_sm = 8, items_factor = 8;
     int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
@@ -874,15 +890,19 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     if (a.n_samples <= 0) return 0;
     const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
     const int want_items = resident_warps * ctx->items_factor;
+    // the last quarter of the (popcount-sorted, i.e. cheapest) terms goes out in 32-term items
+    const int tail_terms = a.nterms >= 128 ? (((a.nterms / 4) + 31) & ~31) : 0;
+    a.tail_start = a.nterms - tail_terms;
+    a.tail_chunks = (tail_terms + 31) / 32;
     int cps = 1;
     if (a.n_samples < want_items) cps = (want_items + a.n_samples - 1) / a.n_samples;
-    int chunk = (a.nterms + cps - 1) / cps;
+    int chunk = (a.tail_start + cps - 1) / cps;
     chunk = (chunk + 31) & ~31;                                // whole groups of 32 terms
     if (chunk < 32) chunk = 32;
-    cps = (a.nterms + chunk - 1) / chunk;
+    cps = (a.tail_start + chunk - 1) / chunk;
     a.chunk = chunk; a.chunks_per_sample = cps;
     const size_t padded = ((size_t)a.nterms + 1) & ~(size_t)1;
-    const unsigned long long items = (unsigned long long)a.n_samples * cps;
+    const unsigned long long items = (unsigned long long)a.n_samples * (cps + a.tail_chunks);
     long long blocks = (long long)ctx->sm_count * ctx->ctas_per_sm;   // persistent CTAs, a multiple of the SM count
     const long long need = (long long)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (blocks > need) blocks = need;
