@@ -891,7 +891,8 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
     const int want_items = resident_warps * ctx->items_factor;
     // the last quarter of the (popcount-sorted, i.e. cheapest) terms goes out in 32-term items
-    const int tail_terms = a.nterms >= 128 ? (((a.nterms / 4) + 31) & ~31) : 0;
+    // (only when samples are scarce: with plenty of samples the big items balance by themselves)
+    const int tail_terms = (a.nterms >= 128 && a.n_samples < want_items) ? (((a.nterms / 4) + 31) & ~31) : 0;
     a.tail_start = a.nterms - tail_terms;
     a.tail_chunks = (tail_terms + 31) / 32;
     int cps = 1;
