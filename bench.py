@@ -144,7 +144,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(0.3)
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -325,34 +325,47 @@ def main():
         ctx.sampled_run()
         results.append(ctx.sampled_finish2(1.0))
 
-    sampler = ClockSampler(local)
-    sampler.start()                      # samples through warm-up + timed region (all under the same load)
+    sampler = ClockSampler(local) if rank == 0 else None      # one nvidia-smi poller per job, not per rank
+    if sampler:
+        sampler.start()              # samples through warm-up + timed region (all under the same load)
     for _ in range(max(3, args.warmup)):
         step_resident()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, prepare_ms, pairs_ms, launches = 0.0, 0.0, 0.0, 0
-    e0.record(tstream)
-    for _ in range(args.steps):
-        step_resident()
+
+    def account():
+        nonlocal kernel_ms, prepare_ms, pairs_ms, launches
         st = ctx.stats()
         kernel_ms += st["kernel_ms"]
         prepare_ms += st["prepare_ms"]
         pairs_ms += st["pairs_ms"]
         launches += st["launches"]
+
+    # K steps, two in flight: the all-reduce + 16-byte read-back of step i overlap the kernels of
+    # step i+1 (every step's result is delivered inside the timed region)
+    e0.record(tstream)
+    ctx.sampled_run()
+    for _ in range(args.steps - 1):
+        ctx.sampled_run()
+        results.append(ctx.sampled_finish2(1.0))
+        account()
+    results.append(ctx.sampled_finish2(1.0))
+    account()
     e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
-    # a timed region of a few ms is shorter than one nvidia-smi poll: keep the same load running
-    # (untimed) until the sampler has at least 3 rows
-    hold = time.perf_counter()
-    while len(sampler.rows) < 3 and time.perf_counter() - hold < 4.0:
-        step_resident()
-    sampler.stop_flag = True
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
+    # a timed region of a few ms is shorter than one nvidia-smi poll: keep the same load running
+    # (untimed; the same number of steps on every rank) so that the sampler sees clocks under load
+    if ms < 1500.0:
+        for _ in range(int(1500.0 / max(ms / args.steps, 0.05)) + 1):
+            step_resident()
+    if sampler:
+        sampler.stop_flag = True
     pairs_per_step = 2 * samples * chi
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
@@ -381,7 +394,7 @@ def main():
     d2h = 2 * 8
 
     if rank == 0:
-        clocks = sampler.summary()
+        clocks = sampler.summary() if sampler else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

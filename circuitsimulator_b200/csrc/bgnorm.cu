@@ -522,8 +522,15 @@ struct bg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t evp[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // per projector: before prepare, after prepare, after pairs
+    // Two job slots so that the all-reduce + read-back of one prepared job overlap the kernels of the
+    // next (bg_sampled_run may be called twice before bg_sampled_finish).  Per slot: timing events,
+    // 8 reduction outputs, 8 counters, one captured graph, one pinned result buffer.
+    int slot = 0;
+    cudaEvent_t ev0s[2] = {nullptr, nullptr}, ev1s[2] = {nullptr, nullptr};
+    cudaEvent_t evps[2][2][3] = {};          // [slot][projector]: before prepare, after prepare, after pairs
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaStream_t cstream = nullptr;          // all-reduce + device->host copies
+    unsigned run_seq = 0, fin_seq = 0;
     int sm_count = 0;
     int rank = 0, world = 1;
     bool allreduce = true;
@@ -556,12 +563,19 @@ struct bg_ctx {
     int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
     // the prepared job replayed as one CUDA graph (BG_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
-    cudaGraphExec_t gexec = nullptr;
-    double* h_out = nullptr;        // pinned: 8 sums + 8 counters
+    cudaGraphExec_t gexecs[2] = {nullptr, nullptr};
+    double* h_out = nullptr;        // pinned: per slot 8 sums + 8 counters
     std::vector<double> bin_sums;
     bg_stats stats;
     std::string err;
 };
+
+#define EV0(ctx) ((ctx)->ev0s[(ctx)->slot])
+#define EV1(ctx) ((ctx)->ev1s[(ctx)->slot])
+#define EVP(ctx, pj, i) ((ctx)->evps[(ctx)->slot][pj][i])
+#define RED(ctx) ((ctx)->d_red + 8 * (ctx)->slot)
+#define CNT(ctx) ((ctx)->d_counters + 8 * (ctx)->slot)
+#define HOUT(ctx) ((ctx)->h_out + 16 * (ctx)->slot)
 
 static int fail(bg_ctx* ctx, const char* fmt, ...) {
     char buf[1024];
@@ -576,7 +590,7 @@ static cudaError_t rec_event(bg_ctx* ctx, cudaEvent_t ev) {
     return ctx->capturing ? cudaEventRecordWithFlags(ev, ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ev, ctx->stream);
 }
 static void drop_graph(bg_ctx* ctx) {
-    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+    for (int sl = 0; sl < 2; sl++) if (ctx->gexecs[sl]) { cudaGraphExecDestroy(ctx->gexecs[sl]); ctx->gexecs[sl] = nullptr; }
 }
 
 template <typename T> static int ensure(bg_ctx* ctx, T** p, size_t* cap, size_t need) {
@@ -617,19 +631,24 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         delete ctx; return r;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaStreamCreate failed"); }
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) cudaEventCreate(&ctx->evp[a][b]);
+    for (int sl = 0; sl < 2; sl++) {
+        cudaEventCreate(&ctx->ev0s[sl]); cudaEventCreate(&ctx->ev1s[sl]);
+        cudaEventCreateWithFlags(&ctx->ev_done[sl], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_out[sl], cudaEventDisableTiming);
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) cudaEventCreate(&ctx->evps[sl][a][b]);
+    }
+    cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking);
     if (cudaMalloc((void**)&ctx->d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaHostAlloc((void**)&ctx->h_out, 16 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->d_red, 8 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_red, 16 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cdf, (BG_MAX_T + 1) * sizeof(double)) != cudaSuccess) {
         int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
-    cudaMemset(ctx->d_red, 0, 8 * sizeof(double));
-    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_red, 0, 16 * sizeof(double));
+    cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
@@ -644,10 +663,15 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     cudaFree(ctx->d_terms); cudaFree(ctx->d_terms_sorted); cudaFree(ctx->d_term_nat); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
     cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) if (ctx->evp[a][b]) cudaEventDestroy(ctx->evp[a][b]);
-    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+    for (int sl = 0; sl < 2; sl++) {
+        if (ctx->ev0s[sl]) cudaEventDestroy(ctx->ev0s[sl]);
+        if (ctx->ev1s[sl]) cudaEventDestroy(ctx->ev1s[sl]);
+        if (ctx->ev_done[sl]) cudaEventDestroy(ctx->ev_done[sl]);
+        if (ctx->ev_out[sl]) cudaEventDestroy(ctx->ev_out[sl]);
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) if (ctx->evps[sl][a][b]) cudaEventDestroy(ctx->evps[sl][a][b]);
+        if (ctx->gexecs[sl]) cudaGraphExecDestroy(ctx->gexecs[sl]);
+    }
+    if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -715,11 +739,12 @@ extern "C" int bg_nccl_join(bg_ctx* ctx, const uint8_t id[128]) {
     return 0;
 }
 
-// all-reduce (sum) n doubles held in ctx->d_red; no-op for world == 1
-static int allreduce_red(bg_ctx* ctx, int n) {
+// all-reduce (sum) n doubles of the current slot's outputs; no-op for world == 1
+static int allreduce_red(bg_ctx* ctx, int n, cudaStream_t stream = nullptr) {
+    if (!stream) stream = ctx->stream;
     if (ctx->world <= 1 || !ctx->allreduce) return 0;
     if (!ctx->nccl_comm) return fail(ctx, "world = %d but bg_nccl_join was not called", ctx->world);
-    int r = g_nccl.AllReduce(ctx->d_red, ctx->d_red, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream);
+    int r = g_nccl.AllReduce(RED(ctx), RED(ctx), (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, stream);
     if (r != 0) return fail(ctx, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     return 0;
 }
@@ -854,9 +879,9 @@ template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepA
 }
 static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
-    CK(cudaMemsetAsync(ctx->d_counters + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(CNT(ctx) + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
     a.force_warp = ctx->force_warp;
-    a.n_warp_routed = ctx->d_counters + 4 * ctx->cur + 2;
+    a.n_warp_routed = CNT(ctx) + 4 * ctx->cur + 2;
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
 
@@ -908,7 +933,7 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     const long long need = (long long)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    unsigned long long* cnt = ctx->d_counters + 4 * ctx->cur;
+    unsigned long long* cnt = CNT(ctx) + 4 * ctx->cur;
     a.pair_count = cnt + 1;
     a.n_warp_routed = cnt + 2;
     a.terms = ctx->d_terms_sorted;
@@ -979,6 +1004,10 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     if (bins < 1) return fail(ctx, "bg_sampled_prepare: bins = %d", bins);
     if (samples < 1) return fail(ctx, "bg_sampled_prepare: samples = 0");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->run_seq != ctx->fin_seq) {            // an unfinished job of the previous configuration
+        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->cstream));
+        ctx->fin_seq = ctx->run_seq;
+    }
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
     if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
@@ -1009,22 +1038,22 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     const uint64_t mine = shard_count(ctx->samples, ctx->rank, ctx->world);
     const int n = (int)mine;
     const int pj = ctx->cur;
-    if (n == 0) { CK(cudaMemsetAsync(ctx->d_red + red_slot, 0, sizeof(double), ctx->stream)); return 0; }
+    if (n == 0) { CK(cudaMemsetAsync(RED(ctx) + red_slot, 0, sizeof(double), ctx->stream)); return 0; }
     PrepArgs pa; memset(&pa, 0, sizeof pa);
     pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = 1; pa.P = ctx->d_P + pj;
     pa.seed = ctx->seeds[pj]; pa.bin = (uint32_t)bin; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
     pa.cdf = ctx->d_cdf;
     pa.zw = ctx->d_zw;
-    CK(rec_event(ctx, ctx->evp[pj][0]));
+    CK(rec_event(ctx, EVP(ctx, pj, 0)));
     if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
-    CK(rec_event(ctx, ctx->evp[pj][1]));
+    CK(rec_event(ctx, EVP(ctx, pj, 1)));
     PairArgs qa; memset(&qa, 0, sizeof qa);
     qa.recs = ctx->d_recs; qa.n_samples = n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
     qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
     if (launch_pairs(ctx, qa)) return 1;
-    CK(rec_event(ctx, ctx->evp[pj][2]));
+    CK(rec_event(ctx, EVP(ctx, pj, 2)));
     ctx->phase_events = true;
-    k_finalize_sum_sampled<<<1, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, ctx->d_red + red_slot);
+    k_finalize_sum_sampled<<<1, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, RED(ctx) + red_slot);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
     return 0;
@@ -1032,13 +1061,25 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
 
 // enqueue the whole prepared job (all projectors, all bins) on ctx's stream
 static int enqueue_job(bg_ctx* ctx) {
-    CK(rec_event(ctx, ctx->ev0));
+    CK(rec_event(ctx, EV0(ctx)));
     for (int pj = 0; pj < ctx->nproj; pj++) {
         ctx->cur = pj;
         for (int b = 0; b < ctx->bins; b++) if (run_bin(ctx, b, 4 * pj + b)) { ctx->cur = 0; return 1; }
     }
     ctx->cur = 0;
-    CK(rec_event(ctx, ctx->ev1));
+    CK(rec_event(ctx, EV1(ctx)));
+    return 0;
+}
+
+// after the job's kernels: all-reduce of the slot's 8 outputs and the read-back, on the side stream
+static int enqueue_collect(bg_ctx* ctx) {
+    const int sl = ctx->slot;
+    CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->cstream, ctx->ev_done[sl], 0));
+    if (allreduce_red(ctx, 8, ctx->cstream)) return 1;          // one all-reduce for every projector and bin
+    CK(cudaMemcpyAsync(HOUT(ctx), RED(ctx), 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->cstream));
+    CK(cudaMemcpyAsync(HOUT(ctx) + 8, CNT(ctx), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->cstream));
+    CK(cudaEventRecord(ctx->ev_out[sl], ctx->cstream));
     return 0;
 }
 
@@ -1047,24 +1088,35 @@ extern "C" int bg_sampled_run(bg_ctx* ctx) {
     if (!ctx->prepared) return fail(ctx, "bg_sampled_run: bg_sampled_prepare not called");
     CK(cudaSetDevice(ctx->device));
     if (ctx->bins > 4) return fail(ctx, "bg_sampled_run: split-phase API supports at most 4 bins (use bg_sampled_norm)");
-    if (!ctx->use_graph) { ctx->stats.launches = 0; return enqueue_job(ctx); }
-    if (!ctx->gexec) {
-        // first run of this job: capture the launch sequence once, replay it afterwards
+    if (ctx->run_seq - ctx->fin_seq >= 2) return fail(ctx, "bg_sampled_run: two jobs already in flight (call bg_sampled_finish)");
+    ctx->slot = (int)(ctx->run_seq & 1u);
+    int rc = 0;
+    if (!ctx->use_graph) {
         ctx->stats.launches = 0;
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        ctx->capturing = true;
-        const int rc = enqueue_job(ctx);
-        ctx->capturing = false;
-        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-        if (rc) { if (g) cudaGraphDestroy(g); return 1; }
-        if (e != cudaSuccess) return fail(ctx, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&ctx->gexec, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) { ctx->gexec = nullptr; return fail(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+        rc = enqueue_job(ctx);
+    } else {
+        cudaGraphExec_t& gexec = ctx->gexecs[ctx->slot];
+        if (!gexec) {
+            // first run of this job in this slot: capture the launch sequence once, replay it afterwards
+            ctx->stats.launches = 0;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            ctx->capturing = true;
+            rc = enqueue_job(ctx);
+            ctx->capturing = false;
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); ctx->slot = 0; return 1; }
+            if (e != cudaSuccess) { ctx->slot = 0; return fail(ctx, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); }
+            e = cudaGraphInstantiate(&gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { gexec = nullptr; ctx->slot = 0; return fail(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+        }
+        CK(cudaGraphLaunch(gexec, ctx->stream));
     }
-    CK(cudaGraphLaunch(ctx->gexec, ctx->stream));
-    ctx->phase_events = true;
+    if (!rc) rc = enqueue_collect(ctx);
+    ctx->slot = 0;
+    if (rc) return 1;
+    ctx->run_seq++;
     return 0;
 }
 
@@ -1082,20 +1134,20 @@ static double median_like_reference(std::vector<double>& v) {
 // after the stream has been synchronised: event times and the pair counters (h_out[8..16))
 static int collect_stats(bg_ctx* ctx, int nproj, bool counters_in_h_out) {
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    CK(cudaEventElapsedTime(&ms, EV0(ctx), EV1(ctx)));
     ctx->stats.kernel_ms = ms;
     ctx->stats.prepare_ms = ctx->stats.pairs_ms = 0;
     if (ctx->phase_events) {
         for (int pj = 0; pj < nproj; pj++) {
             float a = 0, b = 0;
-            if (cudaEventElapsedTime(&a, ctx->evp[pj][0], ctx->evp[pj][1]) == cudaSuccess) ctx->stats.prepare_ms += a;
-            if (cudaEventElapsedTime(&b, ctx->evp[pj][1], ctx->evp[pj][2]) == cudaSuccess) ctx->stats.pairs_ms += b;
+            if (cudaEventElapsedTime(&a, EVP(ctx, pj, 0), EVP(ctx, pj, 1)) == cudaSuccess) ctx->stats.prepare_ms += a;
+            if (cudaEventElapsedTime(&b, EVP(ctx, pj, 1), EVP(ctx, pj, 2)) == cudaSuccess) ctx->stats.pairs_ms += b;
         }
         ctx->phase_events = false;
     }
     unsigned long long c[8];
-    if (counters_in_h_out) memcpy(c, ctx->h_out + 8, sizeof c);
-    else CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (counters_in_h_out) memcpy(c, HOUT(ctx) + 8, sizeof c);
+    else CK(cudaMemcpy(c, CNT(ctx), sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.pairs = 0;
     for (int pj = 0; pj < nproj; pj++) ctx->stats.pairs += c[4 * pj + 1];
     return 0;
@@ -1103,22 +1155,24 @@ static int collect_stats(bg_ctx* ctx, int nproj, bool counters_in_h_out) {
 
 static int sampled_finish_n(bg_ctx* ctx, double* out) {
     if (!ctx) return fail(nullptr, "bg_sampled_finish: null ctx");
-    if (!ctx->prepared) return fail(ctx, "bg_sampled_finish: nothing was run");
+    if (!ctx->prepared || ctx->run_seq == ctx->fin_seq) return fail(ctx, "bg_sampled_finish: nothing was run");
     if (!out) return fail(ctx, "bg_sampled_finish: null out");
     CK(cudaSetDevice(ctx->device));
-    if (allreduce_red(ctx, 8)) return 1;                      // one all-reduce for every projector and bin
-    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_red, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_out + 8, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->slot = (int)(ctx->fin_seq & 1u);                     // the oldest job in flight
+    ctx->fin_seq++;
+    cudaError_t e = cudaEventSynchronize(ctx->ev_out[ctx->slot]);
+    if (e != cudaSuccess) { ctx->slot = 0; return fail(ctx, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)); }
     ctx->stats.d2h_bytes = (uint64_t)ctx->nproj * ctx->bins * sizeof(double);
-    if (ctx->gexec) ctx->stats.launches = (uint64_t)ctx->nproj * ctx->bins * 4;   // prepare, 2 x pairs, finalize per bin
-    if (collect_stats(ctx, ctx->nproj, true)) return 1;
-    for (int pj = 0; pj < ctx->nproj; pj++) {
+    if (ctx->use_graph) ctx->stats.launches = (uint64_t)ctx->nproj * ctx->bins * 4;   // prepare, 2 x pairs, finalize per bin
+    ctx->phase_events = true;
+    const int rc = collect_stats(ctx, ctx->nproj, true);
+    for (int pj = 0; pj < ctx->nproj && !rc; pj++) {
         std::vector<double> v(ctx->bins);
-        for (int b = 0; b < ctx->bins; b++) v[b] = ctx->h_out[4 * pj + b] / (double)ctx->samples;   // total/samples (innerprod.c:83)
+        for (int b = 0; b < ctx->bins; b++) v[b] = HOUT(ctx)[4 * pj + b] / (double)ctx->samples;   // total/samples (innerprod.c:83)
         out[pj] = median_like_reference(v);
     }
-    return 0;
+    ctx->slot = 0;
+    return rc;
 }
 
 extern "C" int bg_sampled_finish(bg_ctx* ctx, double norm, double* out) {
@@ -1147,17 +1201,17 @@ extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samp
     ctx->cur = 0;
     for (int b = 0; b < bins; b++) {
         ctx->stats.launches = 0;
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(cudaEventRecord(EV0(ctx), ctx->stream));
         if (run_bin(ctx, b, 0)) return 1;
-        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventRecord(EV1(ctx), ctx->stream));
         if (allreduce_red(ctx, 1)) return 1;
-        CK(cudaMemcpyAsync(ctx->h_out, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_out + 8, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(HOUT(ctx), RED(ctx), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(HOUT(ctx) + 8, CNT(ctx), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (collect_stats(ctx, 1, true)) return 1;
         total_ms += ctx->stats.kernel_ms; total_pairs += ctx->stats.pairs; launches += ctx->stats.launches;
         prep_ms += ctx->stats.prepare_ms; pair_ms += ctx->stats.pairs_ms;
-        v[b] = ctx->h_out[0] / (double)samples;
+        v[b] = HOUT(ctx)[0] / (double)samples;
     }
     ctx->stats.kernel_ms = total_ms; ctx->stats.pairs = total_pairs; ctx->stats.launches = launches;
     ctx->stats.prepare_ms = prep_ms; ctx->stats.pairs_ms = pair_ms;
@@ -1179,8 +1233,17 @@ extern "C" int bg_sampled_norm2(bg_ctx* ctx, const bg_projector* G, const bg_pro
     }
     if (bg_sampled_prepare2(ctx, G, H, samples, bins, seed_g, seed_h)) return 1;
     ctx->stats.launches = 0;
-    if (enqueue_job(ctx)) return 1;
-    return sampled_finish_n(ctx, out);
+    ctx->slot = (int)(ctx->run_seq & 1u);
+    int rc = enqueue_job(ctx);
+    if (!rc) rc = enqueue_collect(ctx);
+    ctx->slot = 0;
+    if (rc) return 1;
+    ctx->run_seq++;
+    const bool ug = ctx->use_graph;
+    ctx->use_graph = false;                  // launches were counted one by one
+    rc = sampled_finish_n(ctx, out);
+    ctx->use_graph = ug;
+    return rc;
 }
 
 // ---- exact norm ---------------------------------------------------------------------------
@@ -1201,7 +1264,7 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
     CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes = sizeof(bg_projector);
     ctx->stats.launches = 0;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(EV0(ctx), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(double), ctx->stream));
     if (n > 0) {
         PrepArgs pa; memset(&pa, 0, sizeof pa);
@@ -1221,7 +1284,7 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
         CK(cudaGetLastError());
         ctx->stats.launches += 3;
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(EV1(ctx), ctx->stream));
     if (allreduce_red(ctx, 2)) return 1;
     double s[2] = {0, 0};
     CK(cudaMemcpyAsync(s, ctx->d_red, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1261,14 +1324,14 @@ extern "C" int bg_inner_products(bg_ctx* ctx, size_t n_pairs, const bg_state* a,
     CK(cudaMemcpyAsync(da, a, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db, b, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)std::min<size_t>((n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (size_t)ctx->sm_count * 16);
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(EV0(ctx), ctx->stream));
     if (std::max(ta, tb) <= 32) k_inner_products<1><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(da, db, n_pairs, de);
     else k_inner_products<2><<<blocks, 32 * WARPS_PER_BLOCK, 0, ctx->stream>>>(da, db, n_pairs, de);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(EV1(ctx), ctx->stream));
     CK(cudaMemcpyAsync(epm, de, n_pairs * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, EV0(ctx), EV1(ctx));
     ctx->stats.kernel_ms = ms; ctx->stats.pairs = n_pairs; ctx->stats.launches = 1;
     ctx->stats.h2d_bytes = 2 * n_pairs * sizeof(bg_state); ctx->stats.d2h_bytes = n_pairs * 3 * sizeof(int32_t);
     cudaFree(da); cudaFree(db); cudaFree(de);
@@ -1299,7 +1362,7 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
         CK(cudaMemsetAsync(depm, 0, n_states * chi * 3 * sizeof(int32_t), ctx->stream));
     }
     ctx->stats.launches = 0;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(EV0(ctx), ctx->stream));
     PrepArgs pa; memset(&pa, 0, sizeof pa);
     pa.recs = ctx->d_recs; pa.n_samples = n; pa.t = ctx->t; pa.project = project ? 1 : 0; pa.P = ctx->d_P;
     pa.states = dth;
@@ -1313,7 +1376,7 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     k_sum<<<1, 1024, 0, ctx->stream>>>(ctx->d_per, n, ctx->d_red);
     CK(cudaGetLastError());
     ctx->stats.launches += 2;
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(EV1(ctx), ctx->stream));
     double s = 0;
     CK(cudaMemcpyAsync(&s, ctx->d_red, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (per_sample) CK(cudaMemcpyAsync(per_sample, ctx->d_per, n_states * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1463,13 +1526,13 @@ extern "C" int bg_measure_int_peak(bg_ctx* ctx, double* lop3_lane_ops_per_s, dou
     for (int kind = 0; kind < 2; kind++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
-            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            CK(cudaEventRecord(EV0(ctx), ctx->stream));
             if (kind == 0) k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep);
             else k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(ctx->ev1, ctx->stream));
-            CK(cudaEventSynchronize(ctx->ev1));
-            float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            CK(cudaEventRecord(EV1(ctx), ctx->stream));
+            CK(cudaEventSynchronize(EV1(ctx)));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, EV0(ctx), EV1(ctx)));
             if (rep > 0 && ms < best) best = ms;
         }
         const double ops = (double)blocks * threads * (double)iters * 32.0;     // 4 x 8 ops per iteration

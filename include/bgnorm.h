@@ -170,9 +170,10 @@ int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
  * resident: upload (projector, decomposition) once, then run the kernel only.
  * bg_sampled_norm == bg_sampled_prepare + bg_sampled_run + bg_sampled_finish. */
 int  bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed);
-int  bg_sampled_run(bg_ctx* ctx);                       /* async on ctx's stream; the launch sequence is
-                                                           captured once into a CUDA graph and replayed */
-int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* all-reduce, D2H, sync         */
+int  bg_sampled_run(bg_ctx* ctx);                       /* async: kernels on ctx's stream (captured once into a CUDA
+                                                           graph, then replayed), all-reduce + read-back on a side
+                                                           stream.  Up to TWO runs may be in flight.             */
+int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* wait for the OLDEST run in flight     */
 
 /* Numerator and denominator of one probability() evaluation together — both projectors against the
  * same decomposition (libcirc/probability.c:197-198) — with ONE all-reduce and one host sync.

@@ -390,3 +390,22 @@ def test_two_projector_job_and_graph_replay(be):
     be.sampled_prepare2(g, h, 3000, 1, 31, 32)
     be.sampled_run()
     assert be.sampled_finish2(1.0) == (a, b)
+
+
+def test_pipelined_runs_two_in_flight(be):
+    import circuitsimulator_b200 as bg
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
+    be.set_decomposition(cfg["t"], True)
+    g, h = to_bg(G), to_bg(H)
+    want = be.sampled_norm2(g, h, 2000, 1, 7, 8, 1.0)
+    be.sampled_prepare2(g, h, 2000, 1, 7, 8)
+    be.sampled_run()
+    be.sampled_run()
+    with pytest.raises(bg.BGError):
+        be.sampled_run()                      # a third job would overwrite an unread result
+    assert be.sampled_finish2(1.0) == want
+    be.sampled_run()
+    assert be.sampled_finish2(1.0) == want
+    assert be.sampled_finish2(1.0) == want
+    with pytest.raises(bg.BGError):
+        be.sampled_finish2(1.0)               # nothing in flight
