@@ -24,8 +24,11 @@
 struct BgWork { unsigned long long xors, rows, dimers, monomers, basis_changes, pairs; };
 extern BgWork g_bg_work;
 #define BG_WORK(field, n) (g_bg_work.field += (n))
+extern int* g_bg_trace; extern int g_bg_trace_n, g_bg_trace_cap;     // per t_xor2 call: |M1|M2| (lo), (hi)
+#define BG_TRACE(lo, hi) do { if (g_bg_trace && g_bg_trace_n + 2 <= g_bg_trace_cap) { g_bg_trace[g_bg_trace_n++] = (lo); g_bg_trace[g_bg_trace_n++] = (hi); } } while (0)
 #else
 #define BG_WORK(field, n) ((void)0)
+#define BG_TRACE(lo, hi) ((void)0)
 #endif
 
 namespace bg {
@@ -97,6 +100,7 @@ BG_HD int thighest(uint64_t x) {
 // of a warp close together; words are walked in 32-bit halves from the top bit down (FLO + 2 ops).
 BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2) {
     uint32_t U = M1 | M2;
+    BG_TRACE(tpopc(U), 0);
     while (U) {
         const int c = thighest(U);
         const uint32_t b = 1u << c;
@@ -109,6 +113,7 @@ BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
     }
 }
 BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2) {
+    BG_TRACE(tpopc((uint32_t)(M1 | M2)), tpopc((uint32_t)((M1 | M2) >> 32)));
 #pragma unroll
     for (int h = 1; h >= 0; h--) {
         const uint32_t m1 = (uint32_t)(M1 >> (32 * h)), m2 = (uint32_t)(M2 >> (32 * h));

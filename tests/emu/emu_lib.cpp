@@ -45,6 +45,7 @@ void run(const std::function<void()>& body) {
 }  // namespace emu
 
 BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
+int* g_bg_trace = nullptr; int g_bg_trace_n = 0, g_bg_trace_cap = 0;
 using namespace bg;
 
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
@@ -94,6 +95,7 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
                 if (exact) t_term_H<W, false>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, false>(rows, sh, (W)terms[i], e, p, m);
             }
             g_bg_work.pairs++;
+            BG_TRACE(-1, i);                      // end-of-pair marker
             zw_add(z, e, p, m, t / 2 + 1);
             if (epm) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m; }
         }
@@ -131,6 +133,9 @@ int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int
     if (t <= 32) return terms_tpp<1>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
     return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
 }
+
+void emu_trace(int* buf, int cap) { g_bg_trace = buf; g_bg_trace_cap = cap; g_bg_trace_n = 0; }
+int emu_trace_len(void) { return g_bg_trace_n; }
 
 void emu_work_counters(unsigned long long* out, int reset) {
     out[0] = g_bg_work.xors; out[1] = g_bg_work.rows; out[2] = g_bg_work.dimers; out[3] = g_bg_work.monomers;
