@@ -17,7 +17,8 @@
 // samples strided across them, and one NCCL all-reduce of the partial sums.
 //
 // Environment: BG_SEED (default: pid, as probability.c:182), BG_GPUS (default 1),
-//              BG_DEVICE (first device, default 0), BG_QUIETER=1 (drop the chatter).
+//              BG_DEVICE (first device, default 0), BG_QUIETER=1 (drop the chatter),
+//              BG_SERVER=<socket> (forward the stream to a running `bgbackend --serve <socket>`).
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -25,6 +26,13 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -96,7 +104,7 @@ static void random_L(int k, int t, std::vector<uint64_t>& rows) {
 }
 
 // decompose (libcirc/probability.c:307-415): choose |H^t> (exact) or |L> with a random k x t L.
-static void decompose(Config& c, std::vector<uint64_t>& L, double* norm) {
+static void decompose(Config& c, std::vector<uint64_t>& L, double* norm, FILE* out) {
     const int t = c.t;
     if (t == 0) { c.exact = 0; *norm = 1; return; }
     const double v = cos(M_PI / 8);
@@ -106,22 +114,22 @@ static void decompose(Config& c, std::vector<uint64_t>& L, double* norm) {
     const bool forceK = c.k > 0;
     if (!forceK) {
         c.k = (int)ceil(1 - 2 * t * log2(v) - log2(c.fidbound));
-        if (c.verbose) printf("Autopicking k = %d to achieve delta = %f.\n", c.k, c.fidbound);
+        if (c.verbose) fprintf(out, "Autopicking k = %d to achieve delta = %f.\n", c.k, c.fidbound);
     }
     if (c.k > t / 2 && !forceK && !c.forceL) {
-        if (c.verbose) printf("k > t/2. Reverting to exact decomposition.\n");
+        if (c.verbose) fprintf(out, "k > t/2. Reverting to exact decomposition.\n");
         c.exact = 1;
         return;
     }
     if (c.k > t) {
-        if (forceK && !c.quiet) printf("Can't have k > t. Setting k to %d.\n", t);
+        if (forceK && !c.quiet) fprintf(out, "Can't have k > t. Setting k to %d.\n", t);
         c.k = t;
     }
     double overlap = 0, Z_L = 0;
     while (overlap < 1 - c.fidbound || forceK) {
         random_L(c.k, t, L);
         if (c.rank && f2_rank(L) < c.k) {
-            if (!c.quiet) printf("L has insufficient rank. Sampling again...\n");
+            if (!c.quiet) fprintf(out, "L has insufficient rank. Sampling again...\n");
             continue;
         }
         if (!c.fidelity) break;
@@ -135,9 +143,9 @@ static void decompose(Config& c, std::vector<uint64_t>& L, double* norm) {
             Z_L += pow(2, -hamming / 2);
         }
         overlap = pow(2, c.k) * pow(v, 2 * t) / Z_L;
-        if (forceK) { printf("delta = 1 - <H^t|L>: %lf\n", 1 - overlap); break; }
-        if (overlap < 1 - c.fidbound) { if (!c.quiet) printf("delta = 1 - <H^t|L>: %lf - Not good enough!\n", 1 - overlap); }
-        else if (!c.quiet) printf("delta = 1 - <H^t|L>: %lf\n", 1 - overlap);
+        if (forceK) { fprintf(out, "delta = 1 - <H^t|L>: %lf\n", 1 - overlap); break; }
+        if (overlap < 1 - c.fidbound) { if (!c.quiet) fprintf(out, "delta = 1 - <H^t|L>: %lf - Not good enough!\n", 1 - overlap); }
+        else if (!c.quiet) fprintf(out, "delta = 1 - <H^t|L>: %lf\n", 1 - overlap);
     }
     if (c.fidelity) *norm = sqrt(pow(2, c.k) * Z_L);
 }
@@ -151,54 +159,113 @@ static uint64_t splitmix64(uint64_t x) {
 
 struct Job {
     Config c; std::vector<uint64_t> L; double norm; bg_projector G, H; uint64_t seed;
-    int gpus, device0;
-    uint8_t nccl_id[128];
     double numerator = 0, denominator = 0;
     std::string error;
 };
 
-static void worker(Job* job, int rank) {
-    bg_ctx* ctx = nullptr;
-    auto bail = [&](const char* what) {
-        if (rank == 0 || job->error.empty()) job->error = std::string(what) + ": " + bg_last_error(ctx);
+// One context per GPU, each owned by a persistent host thread (the reference's MPI workers,
+// probability.c:221-299, without the processes): created once, reused by every job — in server mode
+// by every probability() call of the front end.
+class Engine {
+public:
+    Engine(int gpus, int device0) : gpus_(gpus), device0_(device0) {}
+    ~Engine() { shutdown(); }
+
+    // returns "" on success
+    std::string start() {
+        if (started_) return "";
+        if (gpus_ > 1 && bg_nccl_unique_id(nccl_id_)) return std::string("bg_nccl_unique_id: ") + bg_last_error(nullptr);
+        ready_ = 0;
+        for (int r = 0; r < gpus_; r++) th_.emplace_back(&Engine::worker, this, r);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return ready_ == gpus_; });
+        started_ = true;
+        return init_error_;
+    }
+
+    void run(Job* job) {
+        std::unique_lock<std::mutex> lk(mu_);
+        job_ = job; done_ = 0; generation_++;
+        cv_job_.notify_all();
+        cv_done_.wait(lk, [&] { return done_ == gpus_; });
+        job_ = nullptr;
+    }
+
+    void shutdown() {
+        if (th_.empty()) return;
+        { std::unique_lock<std::mutex> lk(mu_); stop_ = true; generation_++; cv_job_.notify_all(); }
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    int gpus() const { return gpus_; }
+
+private:
+    void worker(int rank) {
+        bg_ctx* ctx = nullptr;
+        std::string err;
+        if (bg_init(&ctx, device0_ + rank)) err = std::string("bg_init: ") + bg_last_error(nullptr);
+        else if (bg_set_shard(ctx, rank, gpus_)) err = std::string("bg_set_shard: ") + bg_last_error(ctx);
+        else if (gpus_ > 1 && bg_nccl_join(ctx, nccl_id_)) err = std::string("bg_nccl_join: ") + bg_last_error(ctx);
+        unsigned long long seen = 0;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            if (!err.empty() && init_error_.empty()) init_error_ = err;
+            ready_++;
+            cv_done_.notify_all();
+        }
+        while (true) {
+            Job* job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_job_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) break;
+                job = job_;
+            }
+            std::string jerr = err;
+            double num = 0, den = 0;
+            if (jerr.empty()) {
+                const Config& c = job->c;
+                int rc = bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data());
+                if (!rc) {
+                    if (c.noapprox == 0) {            // multiSampledProjector x2 (probability.c:197-198)
+                        double out[2] = {0, 0};
+                        rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
+                                              splitmix64(job->seed + 1), job->norm, out);
+                        num = out[0]; den = out[1];
+                    } else {                          // exactProjector x2 (probability.c:200-201)
+                        rc = bg_exact_norm(ctx, &job->G, job->norm, &num);
+                        if (!rc) rc = bg_exact_norm(ctx, &job->H, job->norm, &den);
+                    }
+                }
+                if (rc) jerr = bg_last_error(ctx);
+            }
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                if (!jerr.empty() && job->error.empty()) job->error = jerr;
+                if (rank == 0) { job->numerator = num; job->denominator = den; }
+                done_++;
+                cv_done_.notify_all();
+            }
+        }
         if (ctx) bg_shutdown(ctx);
-    };
-    if (bg_init(&ctx, job->device0 + rank)) return bail("bg_init");
-    if (bg_set_shard(ctx, rank, job->gpus)) return bail("bg_set_shard");
-    if (job->gpus > 1 && bg_nccl_join(ctx, job->nccl_id)) return bail("bg_nccl_join");
-    const Config& c = job->c;
-    double num = 0, den = 0;
-    if (c.t > 0 && bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data())) return bail("bg_set_decomposition");
-    int rc;
-    if (c.noapprox == 0) {            // multiSampledProjector x2 (probability.c:197-198)
-        rc = bg_sampled_norm(ctx, &job->G, (uint64_t)c.samples, c.bins, splitmix64(job->seed), job->norm, &num);
-        if (!rc) rc = bg_sampled_norm(ctx, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed + 1), job->norm, &den);
-    } else {                          // exactProjector x2 (probability.c:200-201)
-        rc = bg_exact_norm(ctx, &job->G, job->norm, &num);
-        if (!rc) rc = bg_exact_norm(ctx, &job->H, job->norm, &den);
-    }
-    if (rc) return bail("norm evaluation");
-    if (rank == 0) { job->numerator = num; job->denominator = den; }
-    bg_shutdown(ctx);
-}
-
-int main(int argc, char* argv[]) {
-    const bool chatter = getenv("BG_QUIETER") == nullptr;
-    if (chatter) printf("B200 backend (libbgnorm) print mode is on.\n");
-
-    char file[256] = "";
-    if (argc == 1) { if (scanf("%255s", file) != 1) file[0] = 0; }
-    else { strncpy(file, argv[1], 255); file[255] = 0; }
-    FILE* stream;
-    if (strlen(file) == 0 || strcmp(file, "stdin") == 0) {
-        if (chatter) printf("Reading arguments from stdin\n");
-        stream = stdin;
-    } else {
-        if (chatter) printf("Reading arguments from file: %s\n", file);
-        stream = fopen(file, "r");
-        if (!stream) { printf("Error reading file.\n"); return 0; }
     }
 
+    int gpus_, device0_;
+    uint8_t nccl_id_[128];
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_job_, cv_done_;
+    Job* job_ = nullptr;
+    unsigned long long generation_ = 0;
+    int done_ = 0, ready_ = 0;
+    bool stop_ = false, started_ = false;
+    std::string init_error_;
+};
+
+// master() (probability.c:42-216) on one instruction stream: parse, decompose, evaluate, print.
+static void process(FILE* stream, FILE* out, Engine& engine, bool chatter, uint64_t seed) {
+    srand(1);        // decompose() draws L from libc rand() in a fresh process (default seed), probability.c:153,182
     Job job;
     Config& c = job.c;
     bool ok = read_int(stream, &c.quiet) && read_int(stream, &c.verbose) && read_int(stream, &c.noapprox) &&
@@ -206,44 +273,37 @@ int main(int argc, char* argv[]) {
               read_int(stream, &c.k) && read_int(stream, &c.exact) && fscanf(stream, "%lf", &c.fidbound) == 1 &&
               read_int(stream, &c.fidelity) && read_int(stream, &c.rank) && read_int(stream, &c.forceL) &&
               read_int(stream, &c.forceSample);
-    if (!ok) { printf("Error: truncated argument list.\n"); return 0; }
-    if (chatter) printf("samples: %d bins: %d t: %d k: %d exact: %d noapprox: %d\n", c.samples, c.bins, c.t, c.k, c.exact, c.noapprox);
+    if (!ok) { fprintf(out, "Error: truncated argument list.\n"); return; }
+    if (chatter) fprintf(out, "samples: %d bins: %d t: %d k: %d exact: %d noapprox: %d\n", c.samples, c.bins, c.t, c.k, c.exact, c.noapprox);
     std::string perr;
     if (!read_projector(stream, &job.G, &perr) || !read_projector(stream, &job.H, &perr)) {
-        printf("Error: %s.\n", perr.c_str());
-        return 0;
+        fprintf(out, "Error: %s.\n", perr.c_str());
+        return;
     }
-    if (c.t > BG_MAX_T) { printf("Error: t = %d exceeds the 64-qubit limit of the packed layout.\n", c.t); return 0; }
+    if (c.t > BG_MAX_T) { fprintf(out, "Error: t = %d exceeds the 64-qubit limit of the packed layout.\n", c.t); return; }
 
-    decompose(c, job.L, &job.norm);
+    decompose(c, job.L, &job.norm, out);
     if (c.verbose) {
-        if (c.exact) printf("Using exact decomposition of |H^t>: 2^%d\n", (c.t + 1) / 2);
-        else printf("Stabilizer rank of |L>: 2^%d\n", c.k);
+        if (c.exact) fprintf(out, "Using exact decomposition of |H^t>: 2^%d\n", (c.t + 1) / 2);
+        else fprintf(out, "Stabilizer rank of |L>: 2^%d\n", c.k);
     }
     // more samples than terms: fall back to the exact norm (probability.c:162-174)
     if (c.noapprox == 0 && c.forceSample == 0) {
         const double terms = c.exact ? pow(2, (c.t + 1) / 2) : pow(2, c.k);
         if ((double)c.samples * c.bins * 2 > terms - 1) {
             c.noapprox = 1;
-            if (c.verbose) printf("More samples than terms in exact calculation. Disabling sampling.\n");
+            if (c.verbose) fprintf(out, "More samples than terms in exact calculation. Disabling sampling.\n");
         }
     }
     if (!c.exact && chatter) {
-        printf("L:\n");
+        fprintf(out, "L:\n");
         for (int r = 0; r < c.k; r++) {
-            printf(r == 0 ? "[[" : " [");
-            for (int q = 0; q < c.t; q++) printf("%d", (int)((job.L[r] >> q) & 1));
-            printf(r + 1 == c.k ? "]]\n" : "]\n");
+            fprintf(out, r == 0 ? "[[" : " [");
+            for (int q = 0; q < c.t; q++) fprintf(out, "%d", (int)((job.L[r] >> q) & 1));
+            fprintf(out, r + 1 == c.k ? "]]\n" : "]\n");
         }
     }
-
-    const char* es = getenv("BG_SEED");
-    job.seed = es ? strtoull(es, nullptr, 0) : (uint64_t)getpid();
-    const char* eg = getenv("BG_GPUS");
-    job.gpus = eg ? atoi(eg) : 1;
-    if (job.gpus < 1) job.gpus = 1;
-    const char* ed = getenv("BG_DEVICE");
-    job.device0 = ed ? atoi(ed) : 0;
+    job.seed = seed;
 
     double numerator = 0, denominator = 0;
     if (c.t == 0) {
@@ -261,23 +321,145 @@ int main(int argc, char* argv[]) {
             (which ? denominator : numerator) = val;
         }
     } else {
-        if (job.gpus > 1 && bg_nccl_unique_id(job.nccl_id)) { printf("Error: %s\n", bg_last_error(nullptr)); return 0; }
-        if (chatter) printf("World Size: %d\n", job.gpus);
-        std::vector<std::thread> th;
-        for (int r = 1; r < job.gpus; r++) th.emplace_back(worker, &job, r);
-        worker(&job, 0);
-        for (auto& x : th) x.join();
-        if (!job.error.empty()) { printf("Error: %s\n", job.error.c_str()); return 0; }
+        std::string err = engine.start();
+        if (!err.empty()) { fprintf(out, "Error: %s\n", err.c_str()); return; }
+        if (chatter) fprintf(out, "World Size: %d\n", engine.gpus());
+        engine.run(&job);
+        if (!job.error.empty()) { fprintf(out, "Error: %s\n", job.error.c_str()); return; }
         numerator = job.numerator; denominator = job.denominator;
     }
 
     const int sigfigs = 17;
     if (chatter) {
-        printf("|| Gprime |H^t> ||^2 ~= %.*e\n", sigfigs, numerator);
-        printf("|| Hprime |H^t> ||^2 ~= %.*e\n", sigfigs, denominator);
-        if (denominator > 0) printf("Output: %.*e\n", sigfigs, numerator / denominator);
+        fprintf(out, "|| Gprime |H^t> ||^2 ~= %.*e\n", sigfigs, numerator);
+        fprintf(out, "|| Hprime |H^t> ||^2 ~= %.*e\n", sigfigs, denominator);
+        if (denominator > 0) fprintf(out, "Output: %.*e\n", sigfigs, numerator / denominator);
     }
-    printf("%.*e\n", sigfigs, numerator);
-    printf("%.*e\n", sigfigs, denominator);
+    fprintf(out, "%.*e\n", sigfigs, numerator);
+    fprintf(out, "%.*e\n", sigfigs, denominator);
+}
+
+static bool read_all(int fd, std::string* out) {
+    char buf[65536];
+    while (true) {
+        ssize_t n = read(fd, buf, sizeof buf);
+        if (n < 0) { if (errno == EINTR) continue; return false; }
+        if (n == 0) return true;
+        out->append(buf, (size_t)n);
+    }
+}
+static bool write_all(int fd, const char* p, size_t n) {
+    while (n) {
+        ssize_t w = write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        p += w; n -= (size_t)w;
+    }
+    return true;
+}
+
+// Server mode: the front end starts a fresh back-end process for every
+// probability() call (probability.py:244); CUDA + NCCL start-up would then dominate.  `bgbackend --serve
+// <socket>` keeps the contexts alive; a `bgbackend` started with BG_SERVER=<socket> only forwards its
+// instruction stream and relays the answer, so the drop-in protocol is unchanged.
+static int serve(const char* path, int gpus, int device0, bool chatter) {
+    Engine engine(gpus, device0);
+    std::string err = engine.start();
+    if (!err.empty()) { fprintf(stderr, "bgbackend --serve: %s\n", err.c_str()); return 1; }
+    int srv = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (srv < 0) { perror("socket"); return 1; }
+    sockaddr_un addr; memset(&addr, 0, sizeof addr);
+    addr.sun_family = AF_UNIX;
+    strncpy(addr.sun_path, path, sizeof(addr.sun_path) - 1);
+    unlink(path);
+    if (bind(srv, (sockaddr*)&addr, sizeof addr) < 0 || listen(srv, 16) < 0) { perror("bind/listen"); return 1; }
+    printf("bgbackend serving on %s with %d GPU(s)\n", path, gpus);
+    fflush(stdout);
+    uint64_t calls = 0;
+    const char* es = getenv("BG_SEED");
+    const uint64_t seed0 = es ? strtoull(es, nullptr, 0) : (uint64_t)getpid();
+    while (true) {
+        int fd = accept(srv, nullptr, nullptr);
+        if (fd < 0) { if (errno == EINTR) continue; break; }
+        std::string in;
+        if (read_all(fd, &in)) {
+            if (in == "shutdown\n") { close(fd); break; }
+            FILE* fin = fmemopen((void*)in.data(), in.size(), "r");
+            char* obuf = nullptr; size_t olen = 0;
+            FILE* fout = open_memstream(&obuf, &olen);
+            if (chatter) fprintf(fout, "B200 backend (libbgnorm, persistent server) print mode is on.\n");
+            process(fin, fout, engine, chatter, seed0 + 2 * calls++);
+            fclose(fin); fclose(fout);
+            write_all(fd, obuf, olen);
+            free(obuf);
+        }
+        close(fd);
+    }
+    close(srv);
+    unlink(path);
+    return 0;
+}
+
+static bool try_client(const char* path, const std::string& text) {
+    int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (fd < 0) return false;
+    sockaddr_un addr; memset(&addr, 0, sizeof addr);
+    addr.sun_family = AF_UNIX;
+    strncpy(addr.sun_path, path, sizeof(addr.sun_path) - 1);
+    if (connect(fd, (sockaddr*)&addr, sizeof addr) < 0) { close(fd); return false; }
+    bool ok = write_all(fd, text.data(), text.size());
+    shutdown(fd, SHUT_WR);
+    std::string out;
+    ok = ok && read_all(fd, &out);
+    close(fd);
+    if (!ok || out.empty()) return false;
+    fwrite(out.data(), 1, out.size(), stdout);
+    return true;
+}
+
+int main(int argc, char* argv[]) {
+    const bool chatter = getenv("BG_QUIETER") == nullptr;
+    const char* eg = getenv("BG_GPUS");
+    int gpus = eg ? atoi(eg) : 1;
+    if (gpus < 1) gpus = 1;
+    const char* ed = getenv("BG_DEVICE");
+    const int device0 = ed ? atoi(ed) : 0;
+    if (argc >= 3 && strcmp(argv[1], "--serve") == 0) return serve(argv[2], gpus, device0, chatter);
+
+    // argv[1] = file name or "stdin"; without it the first stdin token is the file name (probability.c:52-68)
+    std::string text, file;
+    bool from_stdin = true;
+    if (argc >= 2) file = argv[1];
+    if (argc == 1 || file.empty() || file == "stdin") {
+        if (!read_all(0, &text)) { printf("Error reading stdin.\n"); return 0; }
+        if (argc == 1) {
+            size_t a = text.find_first_not_of(" \t\r\n"), b = a == std::string::npos ? a : text.find_first_of(" \t\r\n", a);
+            file = a == std::string::npos ? "" : text.substr(a, b == std::string::npos ? std::string::npos : b - a);
+            text = b == std::string::npos ? "" : text.substr(b);
+        }
+    }
+    if (!(file.empty() || file == "stdin")) {
+        from_stdin = false;
+        int fd = open(file.c_str(), O_RDONLY);
+        if (fd < 0) { if (chatter) printf("Reading arguments from file: %s\n", file.c_str()); printf("Error reading file.\n"); return 0; }
+        text.clear();
+        read_all(fd, &text);
+        close(fd);
+    }
+    if (const char* srv = getenv("BG_SERVER")) {
+        if (try_client(srv, text)) return 0;          // answered by the persistent server
+    }
+    if (chatter) {
+        printf("B200 backend (libbgnorm) print mode is on.\n");
+        if (from_stdin) printf("Reading arguments from stdin\n");
+        else printf("Reading arguments from file: %s\n", file.c_str());
+    }
+    const char* es = getenv("BG_SEED");
+    const uint64_t seed = es ? strtoull(es, nullptr, 0) : (uint64_t)getpid();
+    Engine engine(gpus, device0);
+    FILE* fin = fmemopen((void*)text.data(), text.size() ? text.size() : 1, "r");
+    process(fin, stdout, engine, chatter, seed);
+    fclose(fin);
+    fflush(stdout);
+    engine.shutdown();
     return 0;
 }

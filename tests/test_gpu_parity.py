@@ -409,3 +409,36 @@ def test_pipelined_runs_two_in_flight(be):
     assert be.sampled_finish2(1.0) == want
     with pytest.raises(bg.BGError):
         be.sampled_finish2(1.0)               # nothing in flight
+
+
+def test_persistent_server_mode(tmp_path):
+    """`bgbackend --serve <socket>` keeps the CUDA contexts alive across probability() calls; a client
+    started with BG_SERVER=<socket> relays the same protocol."""
+    import subprocess
+    import time
+    import circuitsimulator_b200 as bg
+    sock = str(tmp_path / "bg.sock")
+    srv = subprocess.Popen([bg.BACKEND_PATH, "--serve", sock], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        assert b"serving" in srv.stdout.readline()
+        txt = open(os.path.join(GOLDEN, "streams", "toffoli_111.txt")).read()
+        direct = bg.run_backend(txt, env={"BG_SEED": 1})
+        t0 = time.perf_counter()
+        served = [bg.run_backend(txt, env={"BG_SERVER": sock}) for _ in range(3)]
+        dt = (time.perf_counter() - t0) / 3
+        for num, den, _ in served:                       # exact-norm path: deterministic
+            assert num == direct[0] and den == direct[1]
+        # sampled path through the server
+        num, den, _ = bg.run_backend(open(os.path.join(GOLDEN, "streams", "htstack_t4.txt")).read(), env={"BG_SERVER": sock})
+        assert abs(num / den - 0.97855339) < 0.15
+        print("served probability() back-end call: %.1f ms" % (1e3 * dt))
+    finally:
+        import socket as pysock
+        try:
+            c = pysock.socket(pysock.AF_UNIX, pysock.SOCK_STREAM)
+            c.connect(sock)
+            c.sendall(b"shutdown\n")
+            c.close()
+            srv.wait(timeout=20)
+        except Exception:
+            srv.kill()
