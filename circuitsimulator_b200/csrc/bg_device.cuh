@@ -94,6 +94,29 @@ template <int NS> BG_DEV typename WordOf<NS>::T rowb(const typename WordOf<NS>::
     return shflw(x, v & 31);
 }
 
+// Transpose a rows-in-lanes bit matrix in place: out row v, bit u = in row u, bit v.
+// 32 x 32 blocks are transposed with the log-step butterfly (5 x (SHFL.BFLY + 4 LOP3/SHF)); the
+// 64 x 64 case is four such blocks plus a register swap of the off-diagonal ones.
+BG_DEV uint32_t transpose32(uint32_t x) {
+    const int lane = bg_lane();
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j; j >>= 1, m ^= m << j) {
+        const uint32_t y = __shfl_xor_sync(BG_FULL, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+BG_DEV void transposew(uint32_t (&M)[1]) { M[0] = transpose32(M[0]); }
+BG_DEV void transposew(uint64_t (&M)[2]) {
+    const uint32_t a = transpose32((uint32_t)M[0]);            // block (rows 0-31, cols 0-31)
+    const uint32_t b = transpose32((uint32_t)(M[0] >> 32));    // block (rows 0-31, cols 32-63) -> rows 32-63, cols 0-31
+    const uint32_t c = transpose32((uint32_t)M[1]);            // block (rows 32-63, cols 0-31) -> rows 0-31, cols 32-63
+    const uint32_t d = transpose32((uint32_t)(M[1] >> 32));
+    M[0] = ((uint64_t)c << 32) | a;
+    M[1] = ((uint64_t)d << 32) | b;
+}
+
 // ---------------------------------------------------------------- quadratic form
 // q(x) = Q + sum_v D_v x_v + 4 sum_{u<v} J_uv x_u x_v  (mod 8) on the variables v in A.
 // D_v = 2*D1_v + 4*D2_v, J symmetric with J_vv = D1_v (the reference's convention,
@@ -388,25 +411,22 @@ BG_DEV void ambient(const Native<NS>& st, QForm<NS>& o, typename WordOf<NS>::T (
     // R_q = column q of Gbar restricted to the rows in A
     W R[NS];
 #pragma unroll
-    for (int s = 0; s < NS; s++) R[s] = 0;
-    for (int q = 0; q < n; q++) {
-        bool p[NS];
+    for (int s = 0; s < NS; s++) R[s] = st.Gb[s];
+    transposew(R);
 #pragma unroll
-        for (int s = 0; s < NS; s++) p[s] = ((st.Gb[s] >> q) & 1) != 0;
-        const W col = ballotw<NS>(p) & A;
+    for (int s = 0; s < NS; s++) R[s] &= A;
+    // M_q = xor_{a in R_q} J_a ;  t_q = sum_{b<a in R_q} J_ab  (strictly lower rows broadcast separately,
+    // so no per-iteration mask arithmetic; rows outside A are all-zero in R and are skipped)
+    W M[NS], Jlow[NS]; uint32_t tq[NS];
 #pragma unroll
-        for (int s = 0; s < NS; s++) if (lane + 32 * s == q) R[s] = col;
-    }
-    // M_q = xor_{a in R_q} J_a ;  t_q = sum_{b<a in R_q} J_ab
-    W M[NS]; uint32_t tq[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) { M[s] = 0; tq[s] = 0; }
-    for (W rem = A; rem;) {
-        const int a = lowestw(rem); rem &= rem - 1;
+    for (int s = 0; s < NS; s++) { M[s] = 0; tq[s] = 0; Jlow[s] = st.f.J[s] & A & lowmaskw<W>(lane + 32 * s); }
+    for (int a = 0; a < n; a++) {
+        if (!((A >> a) & 1)) continue;
         const W Ja = rowb<NS>(st.f.J, a) & A;
+        const W Jl = rowb<NS>(Jlow, a);
 #pragma unroll
         for (int s = 0; s < NS; s++)
-            if ((R[s] >> a) & 1) { M[s] ^= Ja; tq[s] ^= parw(Ja & R[s] & lowmaskw<W>(a)); }
+            if ((R[s] >> a) & 1) { M[s] ^= Ja; tq[s] ^= parw(Jl & R[s]); }
     }
     bool p1[NS], p2[NS];
 #pragma unroll
@@ -417,15 +437,18 @@ BG_DEV void ambient(const Native<NS>& st, QForm<NS>& o, typename WordOf<NS>::T (
     }
     const W Dt1 = ballotw<NS>(p1) & maskn;
     W Dt2 = ballotw<NS>(p2) & maskn;
-    // J~_qr = parity(M_q & R_r)
+    // J~ = M R^T and R^T = Gbar[A]:  J~_q = xor_{a in M_q} Gbar_a  (M_q only has bits in A)
     W Jt[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) Jt[s] = 0;
-    for (int r = 0; r < n; r++) {
-        const W Rr = rowb<NS>(R, r);
+    for (int a = 0; a < n; a++) {
+        if (!((A >> a) & 1)) continue;
+        const W Ga = rowb<NS>(st.Gb, a);
 #pragma unroll
-        for (int s = 0; s < NS; s++) Jt[s] |= (W)parw(M[s] & Rr) << r;
+        for (int s = 0; s < NS; s++) if ((M[s] >> a) & 1) Jt[s] ^= Ga;
     }
+#pragma unroll
+    for (int s = 0; s < NS; s++) Jt[s] &= maskn;
     // shift u = x + h
     const W h = st.h;
     bool pq[NS], pd[NS];

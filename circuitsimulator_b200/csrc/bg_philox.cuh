@@ -69,15 +69,9 @@ BG_DEV void native_random(Native<NS>& st, int n, uint64_t seed, uint32_t bin, ui
         r[s] = ((A >> v) & 1) ? ((W)philox_half(br, 0) & lowmaskw<W>(v) & A) : 0;     // strictly lower part
         up[s] = 0;
     }
-    for (W rem = A; rem;) {                       // transpose the lower triangle into the upper one
-        const int c = lowestw(rem); rem &= rem - 1;
-        bool p[NS];
 #pragma unroll
-        for (int s = 0; s < NS; s++) p[s] = ((r[s] >> c) & 1) != 0;
-        const W col = ballotw<NS>(p);
-#pragma unroll
-        for (int s = 0; s < NS; s++) if (lane + 32 * s == c) up[s] = col;
-    }
+    for (int s = 0; s < NS; s++) up[s] = r[s];
+    transposew(up);                               // the lower triangle, mirrored into the upper one
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         const int v = lane + 32 * s;
