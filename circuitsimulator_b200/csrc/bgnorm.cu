@@ -443,14 +443,18 @@ __global__ void k_finalize_sampled(const SampleRec* recs, const long long* zw, i
     per_sample[i] = v;
 }
 
-// finalize + fixed-order sum in one single-CTA launch (the same summation order as k_sum over the
-// per-sample values: thread-strided partials, then a binary tree)
+// finalize + fixed-order sum in ONE launch of FIN_BLOCKS CTAs: thread (b, t) adds its samples
+// i = b*1024 + t, + FIN_BLOCKS*1024, ... in order; each CTA tree-reduces to a partial; the CTA that
+// finishes last (atomic ticket) adds the partials in CTA order.  Same bits on every run.
+#define FIN_BLOCKS 32
 __global__ void __launch_bounds__(1024) k_finalize_sum_sampled(const SampleRec* recs, const long long* zw, int n, int t,
-                                                               double* per_sample, double* out) {
+                                                               double* per_sample, double* out, double* partials,
+                                                               unsigned int* ticket) {
     __shared__ double sh[1024];
+    __shared__ bool last;
     const int shf = t / 2 + 1;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) {
+    for (int i = blockIdx.x * 1024 + threadIdx.x; i < n; i += FIN_BLOCKS * 1024) {
         double v = 0.0;
         if (recs[i].alive) {
             double re, im;
@@ -466,7 +470,19 @@ __global__ void __launch_bounds__(1024) k_finalize_sum_sampled(const SampleRec* 
         if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0];
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == FIN_BLOCKS - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double tot = 0.0;
+        for (int b = 0; b < FIN_BLOCKS; b++) tot += ((volatile double*)partials)[b];
+        *out = tot;
+        *ticket = 0u;                    // ready for the next launch
+    }
 }
 
 // exact mode: part_i = pf_i * (diag_i) if i == j, plus (2 pf_i Re(offdiag_i), 0)   (innerprod.c:254-260)
@@ -554,7 +570,9 @@ struct bg_ctx {
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
-    double* d_red = nullptr;                    // [8] reduction outputs
+    double* d_red = nullptr;                    // [2 slots][8] reduction outputs
+    double* d_partials = nullptr;               // [FIN_BLOCKS] per-CTA partial sums of k_finalize_sum_sampled
+    unsigned int* d_ticket = nullptr;
     // prepared sampled run
     int nproj = 1;                  // projectors of the prepared job (2: numerator and denominator together)
     uint64_t samples = 0; int bins = 1; uint64_t seeds[2] = {0, 0};
@@ -642,12 +660,15 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 16 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_partials, 64 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cdf, (BG_MAX_T + 1) * sizeof(double)) != cudaSuccess) {
         int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
     cudaMemset(ctx->d_red, 0, 16 * sizeof(double));
+    cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
     cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
@@ -662,7 +683,7 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     cudaFree(ctx->d_terms); cudaFree(ctx->d_terms_sorted); cudaFree(ctx->d_term_nat); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
-    cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red);
+    cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red); cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket);
     for (int sl = 0; sl < 2; sl++) {
         if (ctx->ev0s[sl]) cudaEventDestroy(ctx->ev0s[sl]);
         if (ctx->ev1s[sl]) cudaEventDestroy(ctx->ev1s[sl]);
@@ -1053,7 +1074,8 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     if (launch_pairs(ctx, qa)) return 1;
     CK(rec_event(ctx, EVP(ctx, pj, 2)));
     ctx->phase_events = true;
-    k_finalize_sum_sampled<<<1, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, RED(ctx) + red_slot);
+    k_finalize_sum_sampled<<<FIN_BLOCKS, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, RED(ctx) + red_slot,
+                                                                  ctx->d_partials, ctx->d_ticket);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
     return 0;
