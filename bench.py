@@ -191,7 +191,8 @@ def run_reference(args, cfgname):
     # bounded sample: every core evaluates `per_core` samples of each projector against `chi_ref`
     # terms.  For |L> workloads the reference is given a smaller k (its own random L): the cost of
     # one inner product does not depend on k, and a full 2 x 512-term sample takes it > 70 s per core.
-    per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds=16.0)
+    # the whole --steps K run is sized to ~2.5 minutes
+    per_core, k_ref, chi_ref = reference_sample(t, exact, k, chi, seconds=max(2.0, min(16.0, 150.0 / (args.steps + 1))))
     text = stream_text(t, per_core, k_ref, exact, G, H)
 
     def step():
