@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
     Rows<W> rows; rows.base = s_rows; rows.stride = blockDim.x;
+    rows.sbase = smem_u32(s_rows); rows.sstride = blockDim.x * (uint32_t)sizeof(W);
 
     const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
     const int sh_ = t / 2 + 1;

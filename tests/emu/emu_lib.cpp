@@ -86,7 +86,7 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
         }
         const bool many = sh.ncons > TPP_MAXC;      // the device routes these to the MANYC instantiation
         W work[128];
-        Rows<W> rows; rows.base = work; rows.stride = 1;
+        Rows<W> rows; rows.base = work; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
             if (many) {
