@@ -832,8 +832,9 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
         std::vector<int32_t> nat(chi);
         for (size_t i = 0; i < chi; i++) nat[i] = (int32_t)i;
         const std::vector<uint64_t>& th = ctx->terms_host;
-        std::stable_sort(nat.begin(), nat.end(), [&](int32_t x, int32_t y) {
-            return __builtin_popcountll(th[x]) > __builtin_popcountll(th[y]); });
+        // key: popcount, then popcount of the low 32-bit half (the row loops walk the two halves separately)
+        auto key = [&](int32_t i) { return (__builtin_popcountll(th[i]) << 8) | __builtin_popcountll(th[i] & 0xffffffffull); };
+        std::stable_sort(nat.begin(), nat.end(), [&](int32_t x, int32_t y) { return key(x) > key(y); });
         std::vector<uint64_t> sorted(padded, 0);
         for (size_t i = 0; i < chi; i++) sorted[i] = th[nat[i]];
         if (ensure(ctx, &ctx->d_terms_sorted, &ctx->d_terms_sorted_cap, padded)) return 1;
