@@ -102,6 +102,21 @@ BG_HD int thighest(uint64_t x) {
 BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2) {
     uint32_t U = M1 | M2;
     BG_TRACE(tpopc(U), 0);
+#if defined(__CUDA_ARCH__)
+    while (U) {
+        const uint32_t c = (uint32_t)thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        const uint32_t addr = c * J.sstride + J.sbase;
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.u32 p, %1, 0;\n\tsetp.ne.u32 q, %2, 0;\n\t"
+            "@p xor.b32 %0, %0, %3;\n\t@q xor.b32 %0, %0, %4;\n\t}"
+            : "+r"(r) : "r"(M1 & b), "r"(M2 & b), "r"(V1), "r"(V2));
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(r) : "memory");
+    }
+#else
     while (U) {
         const int c = thighest(U);
         const uint32_t b = 1u << c;
@@ -112,6 +127,7 @@ BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
         J.put(c, r);
         BG_WORK(rows, 1); BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0));
     }
+#endif
 }
 BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2) {
     BG_TRACE(tpopc((uint32_t)(M1 | M2)), tpopc((uint32_t)((M1 | M2) >> 32)));
@@ -186,6 +202,39 @@ template <typename W> BG_HD void t_pivot(const Rows<W>& J, TF<W>& f, W S, uint32
     f.A &= ~bi;
 }
 
+// The monomer / dimer rounds of the exponential sum on the variables in E (all with D in {0,4}).
+// HI_ONLY (64-bit words): stop as soon as no variable >= 32 is left — the caller continues with
+// 32-bit words on the low halves of the same rows, at half the cost per round.
+template <typename W, bool HI_ONLY>
+BG_HD void t_rounds(const Rows<W>& J, W& E, W& D2, W& Js, uint32_t& cnt, uint32_t& neg0, uint32_t& neg1,
+                    uint32_t& z0, uint32_t& z1, bool has_s) {
+    while (HI_ONLY ? ((uint64_t)E >> 32) != 0 : E != 0) {
+        const int a = thighest(E);
+        const W ba = tbit<W>(a);
+        const W Ja = J.get(a) & E & ~ba;
+        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
+        if (Ja == 0) {                               // monomer {a}
+            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
+            E ^= ba;
+            BG_WORK(monomers, 1);
+            if (z0 && (z1 || !has_s)) { E = 0; break; }      // the whole sum is zero
+            continue;
+        }
+        const int b = thighest(Ja);                  // dimer {a,b}
+        const W bb = tbit<W>(b);
+        const W Jb = J.get(b) & E & ~bb;
+        const W rest = E & ~(ba | bb);
+        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
+        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
+        const W Jar = Ja & rest, Jbr = Jb & rest;
+        BG_WORK(dimers, 1);
+        t_xor2(J, Jar, Jbr, Jbr, Jar);                                  // J_c ^= [J_ca] J_b ^ [J_cb] J_a
+        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
+        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
+        E = rest;
+    }
+}
+
 // sum over F_2^A of e^{i pi q/4}    (bg_device.cuh: expsum)
 template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, int& p, int& m) {
     const W A = f.A;
@@ -203,30 +252,16 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     }
     W D2 = f.D2;
     uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
-    while (E) {
-        const int a = thighest(E);
-        const W ba = tbit<W>(a);
-        const W Ja = J.get(a) & E & ~ba;
-        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
-        if (Ja == 0) {
-            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
-            E ^= ba;
-            BG_WORK(monomers, 1);
-            if (z0 && (z1 || !has_s)) break;
-            continue;
-        }
-        const int b = thighest(Ja);
-        const W bb = tbit<W>(b);
-        const W Jb = J.get(b) & E & ~bb;
-        const W rest = E & ~(ba | bb);
-        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
-        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
-        const W Jar = Ja & rest, Jbr = Jb & rest;
-        BG_WORK(dimers, 1);
-        t_xor2(J, Jar, Jbr, Jbr, Jar);                                  // J_c ^= [J_ca] J_b ^ [J_cb] J_a
-        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
-        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
-        E = rest;
+    if (sizeof(W) == 8) {
+        // variables >= 32 first (the walk is top-down), then everything that is left fits 32-bit words
+        t_rounds<W, true>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
+        Rows<uint32_t> J32;
+        J32.base = reinterpret_cast<uint32_t*>(J.base); J32.stride = 2 * J.stride;
+        J32.sbase = J.sbase; J32.sstride = J.sstride;
+        uint32_t E32 = (uint32_t)E, D32 = (uint32_t)D2, S32 = (uint32_t)Js;
+        t_rounds<uint32_t, false>(J32, E32, D32, S32, cnt, neg0, neg1, z0, z1, has_s);
+    } else {
+        t_rounds<W, false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
     }
     p = 2 * (int)cnt;
     const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
