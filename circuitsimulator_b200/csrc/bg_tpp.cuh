@@ -252,17 +252,10 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     }
     W D2 = f.D2;
     uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
-    if (sizeof(W) == 8) {
-        // variables >= 32 first (the walk is top-down), then everything that is left fits 32-bit words
-        t_rounds<W, true>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
-        Rows<uint32_t> J32;
-        J32.base = reinterpret_cast<uint32_t*>(J.base); J32.stride = 2 * J.stride;
-        J32.sbase = J.sbase; J32.sstride = J.sstride;
-        uint32_t E32 = (uint32_t)E, D32 = (uint32_t)D2, S32 = (uint32_t)Js;
-        t_rounds<uint32_t, false>(J32, E32, D32, S32, cnt, neg0, neg1, z0, z1, has_s);
-    } else {
-        t_rounds<W, false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
-    }
+    // (Measured and rejected: finishing the variables >= 32 first and then continuing with 32-bit words
+    // on the low halves — fewer instructions per lane, but the extra reconvergence point costs more
+    // than it saves: 4.83 vs 4.67 ms at t = 40.)
+    t_rounds<W, false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
     p = 2 * (int)cnt;
     const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
     if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; return; }
