@@ -442,3 +442,62 @@ def test_persistent_server_mode(tmp_path):
             srv.wait(timeout=20)
         except Exception:
             srv.kill()
+
+
+def test_bulk_random_pairs_vs_oracle(be, oracle):
+    """20k generic pairs (device-drawn states, several widths; half of them cut to low dimension) through
+    bg_inner_products against the oracle."""
+    rs = np.random.RandomState(12)
+    total = zeros = 0
+    for t, n in ((5, 4000), (16, 6000), (40, 6000), (64, 4000)):
+        a = be.random_states(t, 31, 0, 0, n)
+        b = be.random_states(t, 32, 0, 0, n)
+        # cut every other b down with random Z-type Paulis (device measurePauli)
+        for _round in range(3):
+            idx = np.arange(0, n, 2)
+            zeta = np.array([int(rs.randint(1, 2 ** 62)) & ((1 << t) - 1) or 1 for _ in idx], dtype=np.uint64)
+            cut, res = be.measure_pauli(b[idx], np.zeros(len(idx), dtype=np.int32), zeta, np.zeros(len(idx), dtype=np.uint64))
+            keep = res > 0
+            b[idx[keep]] = cut[keep]
+        got = be.inner_products(a, b)
+        for i in range(0, n, 1):
+            want = oracle.inner_product(state_from_numpy(a[i]), state_from_numpy(b[i]))
+            assert epm_equal(tuple(got[i]), want), (t, i, tuple(got[i]), want)
+            zeros += want[0] == 0
+        total += n
+    assert total == 20000 and zeros > 500
+
+
+def test_device_rng_law(be, oracle):
+    """The device sampler follows randomStabilizerState's law: the dimension deficit d = t - k has the
+    eq. 79 distribution (chi-square against stabilizer.c:693-716's cdf), h and D bits are fair."""
+    t, n = 16, 60000
+    st = be.random_states(t, 555, 0, 0, n)
+    d = t - st["k"].astype(int)
+    cdf = oracle.dimension_cdf(t)
+    pmf = np.diff(np.concatenate([[0.0], cdf]))
+    chi2 = 0.0
+    for v in range(0, 6):
+        exp = n * pmf[v]
+        obs = int(np.sum(d == v))
+        if exp > 5:
+            chi2 += (obs - exp) ** 2 / exp
+    assert chi2 < 30.0, chi2                      # 5 dof: P(chi2 > 30) ~ 1e-5
+    hbits = np.unpackbits(st["h"].view(np.uint8)).sum() / (n * t)
+    assert abs(hbits - 0.5) < 0.01
+    full = st[st["k"] == t]
+    d1 = np.unpackbits(full["D1"].view(np.uint8)).sum() / (len(full) * t)
+    d2 = np.unpackbits(full["D2"].view(np.uint8)).sum() / (len(full) * t)
+    assert abs(d1 - 0.5) < 0.01 and abs(d2 - 0.5) < 0.01
+    # J symmetric with J_aa = D1_a, off-diagonal bits fair
+    J = full["J"][:, :t]
+    offdiag = 0
+    for a in range(t):
+        col = (J[:, a] >> np.uint64(0))
+        for b in range(a):
+            bit_ab = (J[:, a] >> np.uint64(b)) & np.uint64(1)
+            bit_ba = (J[:, b] >> np.uint64(a)) & np.uint64(1)
+            assert np.array_equal(bit_ab, bit_ba)
+            offdiag += bit_ab.sum()
+        assert np.array_equal((J[:, a] >> np.uint64(a)) & np.uint64(1), (full["D1"] >> np.uint64(a)) & np.uint64(1))
+    assert abs(offdiag / (len(full) * t * (t - 1) / 2) - 0.5) < 0.01
