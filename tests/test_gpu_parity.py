@@ -483,21 +483,21 @@ def test_device_rng_law(be, oracle):
         if exp > 5:
             chi2 += (obs - exp) ** 2 / exp
     assert chi2 < 30.0, chi2                      # 5 dof: P(chi2 > 30) ~ 1e-5
-    hbits = np.unpackbits(st["h"].view(np.uint8)).sum() / (n * t)
+    hbits = np.unpackbits(np.ascontiguousarray(st["h"]).view(np.uint8)).sum() / (n * t)
     assert abs(hbits - 0.5) < 0.01
     full = st[st["k"] == t]
-    d1 = np.unpackbits(full["D1"].view(np.uint8)).sum() / (len(full) * t)
-    d2 = np.unpackbits(full["D2"].view(np.uint8)).sum() / (len(full) * t)
+    d1 = np.unpackbits(np.ascontiguousarray(full["D1"]).view(np.uint8)).sum() / (len(full) * t)
+    d2 = np.unpackbits(np.ascontiguousarray(full["D2"]).view(np.uint8)).sum() / (len(full) * t)
     assert abs(d1 - 0.5) < 0.01 and abs(d2 - 0.5) < 0.01
     # J symmetric with J_aa = D1_a, off-diagonal bits fair
-    J = full["J"][:, :t]
+    J = np.ascontiguousarray(full["J"][:, :t])
+    D1full = np.ascontiguousarray(full["D1"])
     offdiag = 0
     for a in range(t):
-        col = (J[:, a] >> np.uint64(0))
         for b in range(a):
             bit_ab = (J[:, a] >> np.uint64(b)) & np.uint64(1)
             bit_ba = (J[:, b] >> np.uint64(a)) & np.uint64(1)
             assert np.array_equal(bit_ab, bit_ba)
             offdiag += bit_ab.sum()
-        assert np.array_equal((J[:, a] >> np.uint64(a)) & np.uint64(1), (full["D1"] >> np.uint64(a)) & np.uint64(1))
+        assert np.array_equal((J[:, a] >> np.uint64(a)) & np.uint64(1), (D1full >> np.uint64(a)) & np.uint64(1))
     assert abs(offdiag / (len(full) * t * (t - 1) / 2) - 0.5) < 0.01
