@@ -376,4 +376,158 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
     if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
 }
 
+// ---------------------------------------------------------------- left-looking ("lazy") variant
+// The eager routines above update every remaining row of J after each elimination step; the trip
+// counts of those row loops differ from lane to lane (ncu: 20.8 of 32 lanes active), and each touched
+// row costs an LDS + STS + loop overhead.  Every update has the form
+//        row_c ^= [c in M1] V1 ^ [c in M2] V2        with masks that do not depend on the row,
+// so instead of applying it to all rows we only REMEMBER (M1,V1,M2,V2) and materialise a row when it
+// becomes a pivot:  row_c = ambient_c ^ (all remembered updates whose mask contains c).  Per round two
+// rows are materialised, each with a loop over the history whose length is the round number — the
+// SAME for all lanes of a warp.  No per-thread copy of J exists at all; the thread's shared-memory
+// rows hold the dimer history (two words per dimer, at most t/2 dimers).
+// Used for |L> terms with at most LZ_MAXB - 1 parity checks; everything else takes the eager path.
+#define LZ_MAXB 5                      // basis changes kept in registers: up to 4 check pivots + the fold
+template <typename W> struct LzBC { W Sp, Ji, col; };
+
+template <typename W>
+BG_HD W lz_row(const TShared<W>& sh, int c, const LzBC<W> (&bc)[LZ_MAXB], int nb, const Rows<W>& H, int r) {
+    W row = sh.J[c];
+    const W bc_ = tbit<W>(c);
+#pragma unroll
+    for (int j = 0; j < LZ_MAXB; j++) {
+        if (j < nb) {
+            if (bc[j].Sp & bc_) row ^= bc[j].Ji;
+            if (bc[j].col & bc_) row ^= bc[j].Sp;
+        }
+    }
+    for (int q = 0; q < r; q++) {
+        const W X = H.get(2 * q), Y = H.get(2 * q + 1);
+        if (X & bc_) row ^= Y;
+        if (Y & bc_) row ^= X;
+    }
+    BG_WORK(rows, 1); BG_WORK(xors, r);
+    return row;
+}
+
+// x_i = x'_i + sum_{a in Sp} x'_a, remembered instead of applied (cf. t_basis_change)
+template <typename W>
+BG_HD W lz_basis_change(const TShared<W>& sh, TF<W>& f, int i, W Sp, LzBC<W> (&bc)[LZ_MAXB], int& nb, const Rows<W>& H) {
+    const W bi = tbit<W>(i);
+    const W Ji = lz_row<W>(sh, i, bc, nb, H, 0);
+    const W col = (Ji ^ ((Ji & bi) ? Sp : (W)0)) & f.A;
+#pragma unroll
+    for (int j = 0; j < LZ_MAXB; j++) if (j == nb) { bc[j].Sp = Sp; bc[j].Ji = Ji; bc[j].col = col; }
+    nb++;
+    const W d1i = tfill<W>(tget(f.D1, i)), d2i = tfill<W>(tget(f.D2, i));
+    f.D2 ^= Sp & (d2i ^ (d1i & f.D1) ^ Ji);
+    f.D1 ^= Sp & d1i;
+    BG_WORK(basis_changes, 1);
+    return Ji;
+}
+
+template <typename W>
+BG_HD void lz_pivot(const TShared<W>& sh, TF<W>& f, W S, uint32_t beta, LzBC<W> (&bc)[LZ_MAXB], int& nb, const Rows<W>& H) {
+    const int i = thighest(S);
+    const W bi = tbit<W>(i), Sp = S ^ bi;
+    const uint32_t d1 = tget(f.D1, i), d2 = tget(f.D2, i);
+    const W Ji = lz_basis_change<W>(sh, f, i, Sp, bc, nb, H);
+    if (beta) {
+        f.Q = (f.Q + 2u * d1 + 4u * d2) & 7u;
+        f.D2 ^= Ji ^ (Sp & tfill<W>(d1));
+    }
+    f.A &= ~bi;
+}
+
+// <phi|theta> for a |L> term, left-looking.  H: the thread's scratch rows (>= t words).
+// Requires sh.ncons <= LZ_MAXB - 1.
+template <typename W>
+BG_HD void t_term_L_lazy(const Rows<W>& H, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
+    const int t = sh.t;
+    TF<W> f;
+    f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
+    f.A = xt & tlowmask<W>(t);
+    const int k2 = tpopc(f.A);
+    LzBC<W> bc[LZ_MAXB];
+    int nb = 0;
+    // parity checks (cf. t_constraints): earlier pivots are substituted lazily
+    {
+        W hs[LZ_MAXB - 1];
+        uint32_t hb = 0;
+#pragma unroll
+        for (int j = 0; j < LZ_MAXB - 1; j++) {
+            if (j >= sh.ncons) break;
+            W w = sh.cw[j];
+            uint32_t beta = (sh.cbeta >> j) & 1u;
+#pragma unroll
+            for (int q = 0; q < LZ_MAXB - 1; q++) {
+                if (q >= j) break;
+                if (hs[q] && tget(w, thighest(hs[q]))) { w ^= hs[q]; beta ^= (hb >> q) & 1u; }
+            }
+            w &= f.A;
+            hs[j] = w;
+            hb |= beta << j;
+            if (w == 0) { if (beta) { eps = 0; p = 0; m = 0; return; } continue; }
+            lz_pivot<W>(sh, f, w, beta, bc, nb, H);
+        }
+    }
+    // exponential sum (cf. t_expsum / t_rounds)
+    const W A = f.A;
+    const W S = f.D1 & A;
+    const bool has_s = S != 0;
+    W E = A, Js = 0;
+    uint32_t Ds = 0;
+    if (has_s) {
+        const int s = thighest(S);
+        const W bs = tbit<W>(s), Sp = S ^ bs;
+        Ds = 2u + 4u * tget(f.D2, s);
+        if (Sp) lz_basis_change<W>(sh, f, s, Sp, bc, nb, H);
+        E = A & ~bs;
+        Js = lz_row<W>(sh, s, bc, nb, H, 0) & E;
+    }
+    W D2 = f.D2;
+    uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
+    int r = 0;
+    while (E) {
+        const int a = thighest(E);
+        const W ba = tbit<W>(a);
+        const W Ja = lz_row<W>(sh, a, bc, nb, H, r) & E & ~ba;
+        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
+        if (Ja == 0) {
+            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
+            E ^= ba;
+            BG_WORK(monomers, 1);
+            if (z0 && (z1 || !has_s)) break;
+            continue;
+        }
+        const int b = thighest(Ja);
+        const W bb = tbit<W>(b);
+        const W Jb = lz_row<W>(sh, b, bc, nb, H, r) & E & ~bb;
+        const W rest = E & ~(ba | bb);
+        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
+        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
+        const W Jar = Ja & rest, Jbr = Jb & rest;
+        BG_WORK(dimers, 1);
+        H.put(2 * r, Jar); H.put(2 * r + 1, Jbr);                      // remember: row_c ^= [Jar_c] Jbr ^ [Jbr_c] Jar
+        r++;
+        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
+        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
+        E = rest;
+    }
+    p = 2 * (int)cnt;
+    const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
+    if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; }
+    else {
+        const uint32_t m1 = (f.Q + Ds + 4u * neg1) & 7u;
+        if (z0 && z1) { eps = 0; }
+        else {
+            eps = 1;
+            if (z0) m = (int)m1;
+            else if (z1) m = (int)m0;
+            else { p += 1; m = (int)((m0 + ((((m1 - m0) & 7u) == 2u) ? 1u : 7u)) & 7u); }
+        }
+    }
+    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
+}
+
 }  // namespace bg

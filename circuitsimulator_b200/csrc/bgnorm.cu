@@ -91,6 +91,7 @@ struct PairArgs {
     uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
+    int lazy;                                  // |L> terms with few parity checks: left-looking elimination (bg_tpp.cuh)
 };
 
 // work item -> (sample index, term range)
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
             }
         }
         __syncwarp();
+        const bool use_lazy = !EXACT && !MANYC && a.lazy && sh.ncons <= LZ_MAXB - 1;     // warp-uniform
         Zw z, z2;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
                 const W term = (W)terms[i];
                 int e, p, m;
                 if (EXACT) t_term_H<W, MANYC>(rows, sh, term, e, p, m);
+                else if (!MANYC && use_lazy) t_term_L_lazy<W>(rows, sh, term, e, p, m);
                 else t_term_L<W, MANYC>(rows, sh, term, e, p, m);
                 if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
                 else zw_add(z, e, p, m, sh_);
@@ -567,6 +570,7 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
+    int lazy = 1;                   // BG_LAZY=0: always update rows eagerly
     int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
@@ -672,6 +676,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
     cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
+    if (const char* e6 = getenv("BG_LAZY")) ctx->lazy = atoi(e6) != 0;
     if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
@@ -961,6 +966,7 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     a.n_warp_routed = cnt + 2;
     a.terms = ctx->d_terms_sorted;
     a.term_nat = ctx->d_term_nat;
+    a.lazy = ctx->lazy;
     if (!ctx->force_warp) {
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;

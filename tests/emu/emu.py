@@ -58,7 +58,8 @@ class Emu:
         return tuple(out)
 
     def terms(self, theta, P, project, exact, t, terms, tpp=False):
-        """tpp=True: the chi loop through the thread-per-pair code (alive = -1: too many parity checks)."""
+        """tpp=True: the chi loop through the thread-per-pair code; tpp="lazy": its left-looking variant."""
+        self.lib.emu_set_lazy(1 if tpp == "lazy" else 0)
         n = len(terms)
         epm = np.zeros((n, 3), dtype=np.int32)
         npf, k = C.c_int(), C.c_int()

@@ -48,6 +48,7 @@ BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
 int* g_bg_trace = nullptr; int g_bg_trace_n = 0, g_bg_trace_cap = 0;
 using namespace bg;
 
+static int g_emu_lazy = 0;      // 1: use the left-looking variant where the device would
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
 // ambient form is produced by the warp-level code under emulation, each term is then a plain call.
 template <int NS>
@@ -89,7 +90,9 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
         Rows<W> rows; rows.base = work; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
-            if (many) {
+            if (g_emu_lazy && !exact && sh.ncons <= LZ_MAXB - 1) {
+                t_term_L_lazy<W>(rows, sh, (W)terms[i], e, p, m);
+            } else if (many) {
                 if (exact) t_term_H<W, true>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, true>(rows, sh, (W)terms[i], e, p, m);
             } else {
                 if (exact) t_term_H<W, false>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, false>(rows, sh, (W)terms[i], e, p, m);
@@ -134,6 +137,7 @@ int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int
     return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
 }
 
+void emu_set_lazy(int on) { g_emu_lazy = on; }
 void emu_trace(int* buf, int cap) { g_bg_trace = buf; g_bg_trace_cap = cap; g_bg_trace_n = 0; }
 int emu_trace_len(void) { return g_bg_trace_n; }
 
