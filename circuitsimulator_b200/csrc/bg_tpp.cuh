@@ -387,6 +387,9 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
 // SAME for all lanes of a warp.  No per-thread copy of J exists at all; the thread's shared-memory
 // rows hold the dimer history (two words per dimer, at most t/2 dimers).
 // Used for |L> terms with at most LZ_MAXB - 1 parity checks; everything else takes the eager path.
+// Measured (B200, round 1): 5.32 vs 5.78 ms at t = 60 but 5.92 vs 4.67 ms at t = 40, where the unrolled
+// basis-change entries and the history loads cost more than the divergence they remove — so it is an
+// option (BG_LAZY=1), not the default.
 #define LZ_MAXB 5                      // basis changes kept in registers: up to 4 check pivots + the fold
 template <typename W> struct LzBC { W Sp, Ji, col; };
 

@@ -286,7 +286,7 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
     return (long long)(((unsigned long long)hi << 32) | lo);
 }
 
-template <typename W, bool EXACT, bool TRI, bool MANYC>
+template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
 __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
             }
         }
         __syncwarp();
-        const bool use_lazy = !EXACT && !MANYC && a.lazy && sh.ncons <= LZ_MAXB - 1;     // warp-uniform
+        const bool use_lazy = LAZY && !EXACT && !MANYC && sh.ncons <= LZ_MAXB - 1;     // warp-uniform
         Zw z, z2;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
                 const W term = (W)terms[i];
                 int e, p, m;
                 if (EXACT) t_term_H<W, MANYC>(rows, sh, term, e, p, m);
-                else if (!MANYC && use_lazy) t_term_L_lazy<W>(rows, sh, term, e, p, m);
+                else if (LAZY && use_lazy) t_term_L_lazy<W>(rows, sh, term, e, p, m);
                 else t_term_L<W, MANYC>(rows, sh, term, e, p, m);
                 if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
                 else zw_add(z, e, p, m, sh_);
@@ -570,7 +570,7 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
-    int lazy = 1;                   // BG_LAZY=0: always update rows eagerly
+    int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (wins at t = 60, loses at t = 40)
     int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     bg_projector* d_P = nullptr;
@@ -922,18 +922,19 @@ template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const Pair
     return 0;
 }
 
-template <typename W, bool EXACT, bool TRI, bool MANYC>
+template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
 static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
     if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pairs_tpp<W, EXACT, TRI, MANYC><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
+        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     return 0;
 }
 template <typename W, bool MANYC> static int launch_tpp_w(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
-    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false, MANYC>(ctx, a, blocks, smem);
-    return a.tri ? launch_tpp_inst<W, false, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false, MANYC>(ctx, a, blocks, smem);
+    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true, MANYC, false>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false, MANYC, false>(ctx, a, blocks, smem);
+    if (!MANYC && ctx->lazy && !a.tri) return launch_tpp_inst<W, false, false, false, true>(ctx, a, blocks, smem);
+    return a.tri ? launch_tpp_inst<W, false, true, MANYC, false>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false, MANYC, false>(ctx, a, blocks, smem);
 }
 
 // Fill in chunking / staging and launch the pair kernels: k_pairs_tpp for the samples routed to it,
