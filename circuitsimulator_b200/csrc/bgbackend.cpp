@@ -263,23 +263,46 @@ private:
     std::string init_error_;
 };
 
-// master() (probability.c:42-216) on one instruction stream: parse, decompose, evaluate, print.
-static void process(FILE* stream, FILE* out, Engine& engine, bool chatter, uint64_t seed) {
-    srand(1);        // decompose() draws L from libc rand() in a fresh process (default seed), probability.c:153,182
-    Job job;
+// The 13 scalars and two projectors of one instruction stream (probability.c:74-127).  Reads token by
+// token and never waits for end-of-file: the front end keeps the pipe open (probability.py:283-284).
+static bool parse_job(FILE* stream, Job& job, std::string* err) {
     Config& c = job.c;
     bool ok = read_int(stream, &c.quiet) && read_int(stream, &c.verbose) && read_int(stream, &c.noapprox) &&
               read_int(stream, &c.samples) && read_int(stream, &c.bins) && read_int(stream, &c.t) &&
               read_int(stream, &c.k) && read_int(stream, &c.exact) && fscanf(stream, "%lf", &c.fidbound) == 1 &&
               read_int(stream, &c.fidelity) && read_int(stream, &c.rank) && read_int(stream, &c.forceL) &&
               read_int(stream, &c.forceSample);
-    if (!ok) { fprintf(out, "Error: truncated argument list.\n"); return; }
-    if (chatter) fprintf(out, "samples: %d bins: %d t: %d k: %d exact: %d noapprox: %d\n", c.samples, c.bins, c.t, c.k, c.exact, c.noapprox);
-    std::string perr;
-    if (!read_projector(stream, &job.G, &perr) || !read_projector(stream, &job.H, &perr)) {
-        fprintf(out, "Error: %s.\n", perr.c_str());
-        return;
+    if (!ok) { *err = "truncated argument list"; return false; }
+    if (!read_projector(stream, &job.G, err) || !read_projector(stream, &job.H, err)) return false;
+    return true;
+}
+
+// the same stream, re-serialised (what a client forwards to the persistent server)
+static std::string serialize_job(const Job& job) {
+    const Config& c = job.c;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%d %d %d %d %d %d %d %d %.17g %d %d %d %d\n", c.quiet, c.verbose, c.noapprox, c.samples,
+             c.bins, c.t, c.k, c.exact, c.fidbound, c.fidelity, c.rank, c.forceL, c.forceSample);
+    std::string out = buf;
+    for (const bg_projector* P : {&job.G, &job.H}) {
+        out += std::to_string(P->nstabs) + " " + std::to_string(P->nstabs ? P->nqubits : 0) + "\n";
+        for (int i = 0; i < P->nstabs; i++) {
+            out += std::to_string((int)P->phase[i]);
+            for (int q = 0; q < P->nqubits; q++) {
+                out += ((P->xs[i] >> q) & 1) ? " 1" : " 0";
+                out += ((P->zs[i] >> q) & 1) ? " 1" : " 0";
+            }
+            out += "\n";
+        }
     }
+    return out;
+}
+
+// master() (probability.c:42-216) on one parsed instruction stream: decompose, evaluate, print.
+static void process(Job& job, FILE* out, Engine& engine, bool chatter, uint64_t seed) {
+    srand(1);        // decompose() draws L from libc rand() in a fresh process (default seed), probability.c:153,182
+    Config& c = job.c;
+    if (chatter) fprintf(out, "samples: %d bins: %d t: %d k: %d exact: %d noapprox: %d\n", c.samples, c.bins, c.t, c.k, c.exact, c.noapprox);
     if (c.t > BG_MAX_T) { fprintf(out, "Error: t = %d exceeds the 64-qubit limit of the packed layout.\n", c.t); return; }
 
     decompose(c, job.L, &job.norm, out);
@@ -387,7 +410,9 @@ static int serve(const char* path, int gpus, int device0, bool chatter) {
             char* obuf = nullptr; size_t olen = 0;
             FILE* fout = open_memstream(&obuf, &olen);
             if (chatter) fprintf(fout, "B200 backend (libbgnorm, persistent server) print mode is on.\n");
-            process(fin, fout, engine, chatter, seed0 + 2 * calls++);
+            Job job; std::string perr;
+            if (!parse_job(fin, job, &perr)) fprintf(fout, "Error: %s.\n", perr.c_str());
+            else process(job, fout, engine, chatter, seed0 + 2 * calls++);
             fclose(fin); fclose(fout);
             write_all(fd, obuf, olen);
             free(obuf);
@@ -426,39 +451,29 @@ int main(int argc, char* argv[]) {
     if (argc >= 3 && strcmp(argv[1], "--serve") == 0) return serve(argv[2], gpus, device0, chatter);
 
     // argv[1] = file name or "stdin"; without it the first stdin token is the file name (probability.c:52-68)
-    std::string text, file;
-    bool from_stdin = true;
-    if (argc >= 2) file = argv[1];
-    if (argc == 1 || file.empty() || file == "stdin") {
-        if (!read_all(0, &text)) { printf("Error reading stdin.\n"); return 0; }
-        if (argc == 1) {
-            size_t a = text.find_first_not_of(" \t\r\n"), b = a == std::string::npos ? a : text.find_first_of(" \t\r\n", a);
-            file = a == std::string::npos ? "" : text.substr(a, b == std::string::npos ? std::string::npos : b - a);
-            text = b == std::string::npos ? "" : text.substr(b);
-        }
+    char file[256] = "";
+    if (argc == 1) { if (scanf("%255s", file) != 1) file[0] = 0; }
+    else { strncpy(file, argv[1], 255); file[255] = 0; }
+    const bool from_stdin = strlen(file) == 0 || strcmp(file, "stdin") == 0;
+    FILE* stream = stdin;
+    if (!from_stdin) {
+        stream = fopen(file, "r");
+        if (!stream) { if (chatter) printf("Reading arguments from file: %s\n", file); printf("Error reading file.\n"); return 0; }
     }
-    if (!(file.empty() || file == "stdin")) {
-        from_stdin = false;
-        int fd = open(file.c_str(), O_RDONLY);
-        if (fd < 0) { if (chatter) printf("Reading arguments from file: %s\n", file.c_str()); printf("Error reading file.\n"); return 0; }
-        text.clear();
-        read_all(fd, &text);
-        close(fd);
-    }
+    Job job; std::string perr;
+    if (!parse_job(stream, job, &perr)) { printf("Error: %s.\n", perr.c_str()); return 0; }
     if (const char* srv = getenv("BG_SERVER")) {
-        if (try_client(srv, text)) return 0;          // answered by the persistent server
+        if (try_client(srv, serialize_job(job))) return 0;          // answered by the persistent server
     }
     if (chatter) {
         printf("B200 backend (libbgnorm) print mode is on.\n");
         if (from_stdin) printf("Reading arguments from stdin\n");
-        else printf("Reading arguments from file: %s\n", file.c_str());
+        else printf("Reading arguments from file: %s\n", file);
     }
     const char* es = getenv("BG_SEED");
     const uint64_t seed = es ? strtoull(es, nullptr, 0) : (uint64_t)getpid();
     Engine engine(gpus, device0);
-    FILE* fin = fmemopen((void*)text.data(), text.size() ? text.size() : 1, "r");
-    process(fin, stdout, engine, chatter, seed);
-    fclose(fin);
+    process(job, stdout, engine, chatter, seed);
     fflush(stdout);
     engine.shutdown();
     return 0;

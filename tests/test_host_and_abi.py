@@ -120,3 +120,60 @@ def test_strided_sharding_world2_gloo(oracle):
     whole, _ = oracle.sampled_sum_philox(G, True, [], 9, 0, 0, 1, 37)
     assert count == 37
     assert abs(total - whole) <= 1e-13 * abs(whole)
+
+
+def test_backend_answers_without_eof_on_stdin():
+    """The front end writes the stream and keeps the pipe open (libcirc/probability.py:283-291): the back
+    end must answer after the last token, not at end-of-file."""
+    import select
+    import time
+    bg = _built()
+    p = subprocess.Popen([bg.BACKEND_PATH, "stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        p.stdin.write(b"0 0 0 100 1 0 0 1 1e-5 0 0 0 0\n2 0 0 2\n1 0 0\n")
+        p.stdin.flush()                                   # NOT closed
+        deadline, buf = time.time() + 20, b""
+        while time.time() < deadline and p.poll() is None:
+            r, _, _ = select.select([p.stdout], [], [], 0.5)
+            if r:
+                chunk = os.read(p.stdout.fileno(), 65536)
+                if not chunk:
+                    break
+                buf += chunk
+        if p.poll() is None:
+            p.wait(timeout=5)
+        buf += p.stdout.read()
+        lines = buf.decode().splitlines()
+        assert abs(float(lines[-2]) - 1 / 3) < 1e-15 and float(lines[-1]) == 1.0
+    finally:
+        if p.poll() is None:
+            p.kill()
+
+
+def test_unmodified_front_end_drives_the_backend():
+    """libcirc.probability() of the reference (when its tree is present) spawns bgbackend through
+    cpath/mpirun, feeds it the token stream and parses the answer.  Without a GPU the back end answers
+    with an Error line and the front end raises RuntimeError (probability.py:302-312) — no hang, no
+    silent fallback; with a GPU it returns the probability."""
+    ref = os.environ.get("BG_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "libcirc")):
+        pytest.skip("reference tree not present")
+    bg = _built()
+    code = (
+        "import sys, warnings; warnings.simplefilter('ignore'); sys.path.insert(0, %r)\n"
+        "from libcirc.probability import probability\n"
+        "from libcirc.compile.compilecirc import compileCircuit\n"
+        "c = compileCircuit(fname='circuits/HTstack.circ')\n"
+        "try:\n"
+        "    p = probability(c, {0: 0}, config={'samples': 512, 'forceSample': True, 'quiet': True,\n"
+        "                    'cpath': %r, 'mpirun': '/usr/bin/env'})\n"
+        "    print('PROB', p)\n"
+        "except RuntimeError:\n"
+        "    print('RUNTIMEERROR')\n" % (ref, bg.BACKEND_PATH))
+    out = subprocess.run([sys.executable, "-c", code], cwd=ref, capture_output=True, text=True, timeout=120).stdout
+    import torch
+    if torch.cuda.is_available():
+        prob = float([ln for ln in out.splitlines() if ln.startswith("PROB")][0].split()[1])
+        assert abs(prob - 0.97855339) < 0.2
+    else:
+        assert "RUNTIMEERROR" in out and "no CPU fallback" in out
