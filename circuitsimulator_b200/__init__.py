@@ -98,6 +98,7 @@ def load_library():
         "bg_sampled_finish2": [vp, dbl, _P(dbl)],
         "bg_set_stream": [vp, vp],
         "bg_measure_int_peak": [vp, _P(dbl), _P(dbl)],
+        "bg_decomposition_weights": [vp, i32, i32, _P(u64), _P(u64)],
     }
     for name, args in sig.items():
         f = getattr(lib, name)
@@ -118,7 +119,7 @@ def exported_symbols():
             "bg_sampled_norm", "bg_exact_norm", "bg_inner_products", "bg_sampled_norm_from_states",
             "bg_measure_pauli", "bg_random_states", "bg_decomposition_terms", "bg_get_stats",
             "bg_sampled_prepare", "bg_sampled_run", "bg_sampled_finish", "bg_sampled_norm2", "bg_sampled_prepare2",
-            "bg_sampled_finish2", "bg_set_stream", "bg_measure_int_peak"]
+            "bg_sampled_finish2", "bg_set_stream", "bg_measure_int_peak", "bg_decomposition_weights"]
 
 
 def _states_arg(arr):
@@ -260,6 +261,15 @@ class Backend:
         a, b = C.c_double(), C.c_double()
         self._ck(self.lib.bg_measure_int_peak(self.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def decomposition_weights(self, t, L_rows):
+        """decompose()'s fidelity loop (libcirc/probability.c:373-391) on the device: hist[w] = number of
+        the 2^k combinations of the rows of L with Hamming weight w."""
+        k = len(L_rows)
+        rows = (C.c_uint64 * max(k, 1))(*[int(r) for r in L_rows])
+        hist = (C.c_uint64 * 65)()
+        self._ck(self.lib.bg_decomposition_weights(self.ctx, t, k, rows, hist))
+        return [int(v) for v in hist]
 
     def stats(self):
         s = Stats()

@@ -34,13 +34,30 @@ extern int* g_bg_trace; extern int g_bg_trace_n, g_bg_trace_cap;     // per t_xo
 namespace bg {
 
 // per-thread view of its working rows: row r lives at base[r * stride]
+#if defined(__CUDA_ARCH__)
+// one IMAD for the address, LDS/STS on the 32-bit shared-memory window (no generic-pointer arithmetic)
+BG_HD void t_lds(uint32_t addr, uint32_t& v) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); }
+BG_HD void t_lds(uint32_t addr, uint64_t& v) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+    v = ((uint64_t)hi << 32) | lo;
+}
+BG_HD void t_sts(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+BG_HD void t_sts(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)) : "memory");
+}
+#endif
 template <typename W> struct Rows {
     W* base;
     int stride;
     uint32_t sbase, sstride;     // device: shared-memory byte address of row 0, byte stride between rows
+#if defined(__CUDA_ARCH__)
+    BG_HDM W get(int r) const { W v; t_lds((uint32_t)r * sstride + sbase, v); return v; }
+    BG_HDM void put(int r, W v) const { t_sts((uint32_t)r * sstride + sbase, v); }
+#else
     BG_HDM W get(int r) const { return base[(size_t)r * stride]; }
     BG_HDM void put(int r, W v) const { base[(size_t)r * stride] = v; }
-    BG_HDM void xr(int r, W v) const { base[(size_t)r * stride] ^= v; }
+#endif
 };
 
 template <typename W> struct TF {      // per-thread quadratic form scalars (J is in Rows)
@@ -93,7 +110,7 @@ BG_HD int thighest(uint32_t x) {
 }
 BG_HD int thighest(uint64_t x) {
     const uint32_t hi = (uint32_t)(x >> 32);
-    return hi ? 32 + thighest(hi) : thighest((uint32_t)x);
+    return thighest(hi ? hi : (uint32_t)x) + (hi ? 32 : 0);          // selects, no branch: one FLO
 }
 
 // row_c ^= [c in M1] V1 ^ [c in M2] V2  for every c in M1 | M2 — the one primitive every step of the
@@ -174,6 +191,89 @@ BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2
 #endif
 }
 
+// Two elimination steps at once:  row_c ^= [c in M1] V1 ^ [c in M2] V2 ^ [c in M3] V3 ^ [c in M4] V4.
+// A row is touched when ANY of its four bits is set (15/16 of the remaining rows instead of 3/4 twice), so
+// the trip counts of the 32 lanes of a warp are nearly equal and each row is loaded and stored once.
+BG_HD void t_xor4(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2,
+                  uint32_t M3, uint32_t V3, uint32_t M4, uint32_t V4) {
+    uint32_t U = M1 | M2 | M3 | M4;
+    BG_TRACE(tpopc(U), 0);
+#if defined(__CUDA_ARCH__)
+    while (U) {
+        const uint32_t c = (uint32_t)thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        const uint32_t addr = c * J.sstride + J.sbase;
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+        asm("{\n\t.reg .pred p, q, r, s;\n\t"
+            "setp.ne.u32 p, %1, 0;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\tsetp.ne.u32 s, %4, 0;\n\t"
+            "@p xor.b32 %0, %0, %5;\n\t@q xor.b32 %0, %0, %6;\n\t@r xor.b32 %0, %0, %7;\n\t@s xor.b32 %0, %0, %8;\n\t}"
+            : "+r"(r) : "r"(M1 & b), "r"(M2 & b), "r"(M3 & b), "r"(M4 & b), "r"(V1), "r"(V2), "r"(V3), "r"(V4));
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(r) : "memory");
+    }
+#else
+    while (U) {
+        const int c = thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        uint32_t r = J.get(c);
+        if (M1 & b) r ^= V1;
+        if (M2 & b) r ^= V2;
+        if (M3 & b) r ^= V3;
+        if (M4 & b) r ^= V4;
+        J.put(c, r);
+        BG_WORK(rows, 1); BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0) + ((M3 & b) ? 1 : 0) + ((M4 & b) ? 1 : 0));
+    }
+#endif
+}
+BG_HD void t_xor4(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2,
+                  uint64_t M3, uint64_t V3, uint64_t M4, uint64_t V4) {
+    BG_TRACE(tpopc((uint32_t)(M1 | M2 | M3 | M4)), tpopc((uint32_t)((M1 | M2 | M3 | M4) >> 32)));
+#if defined(__CUDA_ARCH__)
+    const uint32_t v1l = (uint32_t)V1, v1h = (uint32_t)(V1 >> 32), v2l = (uint32_t)V2, v2h = (uint32_t)(V2 >> 32);
+    const uint32_t v3l = (uint32_t)V3, v3h = (uint32_t)(V3 >> 32), v4l = (uint32_t)V4, v4h = (uint32_t)(V4 >> 32);
+#pragma unroll
+    for (int h = 1; h >= 0; h--) {
+        const uint32_t m1 = (uint32_t)(M1 >> (32 * h)), m2 = (uint32_t)(M2 >> (32 * h));
+        const uint32_t m3 = (uint32_t)(M3 >> (32 * h)), m4 = (uint32_t)(M4 >> (32 * h));
+        const uint32_t hbase = J.sbase + (uint32_t)(32 * h) * J.sstride;
+        uint32_t U = m1 | m2 | m3 | m4;
+        while (U) {
+            const uint32_t c = (uint32_t)thighest(U);
+            const uint32_t b = 1u << c;
+            U ^= b;
+            const uint32_t addr = c * J.sstride + hbase;
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+            asm("{\n\t.reg .pred p, q, r, s;\n\t"
+                "setp.ne.u32 p, %2, 0;\n\tsetp.ne.u32 q, %3, 0;\n\tsetp.ne.u32 r, %4, 0;\n\tsetp.ne.u32 s, %5, 0;\n\t"
+                "@p xor.b32 %0, %0, %6;\n\t@p xor.b32 %1, %1, %7;\n\t"
+                "@q xor.b32 %0, %0, %8;\n\t@q xor.b32 %1, %1, %9;\n\t"
+                "@r xor.b32 %0, %0, %10;\n\t@r xor.b32 %1, %1, %11;\n\t"
+                "@s xor.b32 %0, %0, %12;\n\t@s xor.b32 %1, %1, %13;\n\t}"
+                : "+r"(lo), "+r"(hi) : "r"(m1 & b), "r"(m2 & b), "r"(m3 & b), "r"(m4 & b),
+                  "r"(v1l), "r"(v1h), "r"(v2l), "r"(v2h), "r"(v3l), "r"(v3h), "r"(v4l), "r"(v4h));
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(lo), "r"(hi) : "memory");
+        }
+    }
+#else
+    uint64_t U = M1 | M2 | M3 | M4;
+    while (U) {
+        const int c = thighest(U);
+        const uint64_t b = 1ull << c;
+        U ^= b;
+        uint64_t r = J.get(c);
+        if (M1 & b) r ^= V1;
+        if (M2 & b) r ^= V2;
+        if (M3 & b) r ^= V3;
+        if (M4 & b) r ^= V4;
+        J.put(c, r);
+        BG_WORK(rows, 1); BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0) + ((M3 & b) ? 1 : 0) + ((M4 & b) ? 1 : 0));
+    }
+#endif
+}
+
 // x_i = x'_i + sum_{a in Sp} x'_a.   (bg_device.cuh: basis_change)   Returns the old row i.
 template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, W Sp) {
     const W bi = tbit<W>(i);
@@ -202,37 +302,175 @@ template <typename W> BG_HD void t_pivot(const Rows<W>& J, TF<W>& f, W S, uint32
     f.A &= ~bi;
 }
 
-// The monomer / dimer rounds of the exponential sum on the variables in E (all with D in {0,4}).
-// HI_ONLY (64-bit words): stop as soon as no variable >= 32 is left — the caller continues with
-// 32-bit words on the low halves of the same rows, at half the cost per round.
-template <typename W, bool HI_ONLY>
+// One elimination step's bookkeeping: variable a (bit ba) with partner b (bit bb; = ba for a monomer),
+// M1 / M2 = the remaining rows c with J_ca / J_cb.  `on` = false turns the step into a no-op.
+template <typename W>
+BG_HD void t_step_scalars(W& D2, W& Js, W ba, W bb, bool on, bool dimer, W M1, W M2,
+                          uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1) {
+    const bool d2a = (D2 & ba) != 0, sa = (Js & ba) != 0;
+    const bool d2b = (D2 & bb) != 0, sb = (Js & bb) != 0;
+    cnt += on ? 1u : 0u;
+    neg0 ^= (uint32_t)(dimer & d2a & d2b);
+    neg1 ^= (uint32_t)(dimer & (d2a ^ sa) & (d2b ^ sb));
+    z0 |= (uint32_t)(on & !dimer & d2a);
+    z1 |= (uint32_t)(on & !dimer & (d2a ^ sa));
+    D2 ^= (d2b ? M1 : (W)0) ^ (d2a ? M2 : (W)0) ^ (M1 & M2);
+    Js ^= (sb ? M1 : (W)0) ^ (sa ? M2 : (W)0);
+}
+
+// The monomer / dimer steps of the exponential sum on the variables in E (all with D in {0,4}), TWO steps
+// per pass over the rows.  No branch in the body: a monomer {a} is a dimer whose update masks are empty,
+// and a missing second step is a step with all masks empty — the 32 lanes of a warp stay together, only
+// the row loop of t_xor4 has per-lane trip counts.  Step 2 picks its variables from the rows a2, b2
+// brought up to date with step 1 on the fly; every other remaining row gets both updates in one touch.
+template <typename W>
 BG_HD void t_rounds(const Rows<W>& J, W& E, W& D2, W& Js, uint32_t& cnt, uint32_t& neg0, uint32_t& neg1,
                     uint32_t& z0, uint32_t& z1, bool has_s) {
-    while (HI_ONLY ? ((uint64_t)E >> 32) != 0 : E != 0) {
+    while (E != 0) {
+        // ---- step 1: a = highest variable left, b = its highest neighbour
         const int a = thighest(E);
         const W ba = tbit<W>(a);
         const W Ja = J.get(a) & E & ~ba;
-        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
-        if (Ja == 0) {                               // monomer {a}
-            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
-            E ^= ba;
-            BG_WORK(monomers, 1);
-            if (z0 && (z1 || !has_s)) { E = 0; break; }      // the whole sum is zero
-            continue;
-        }
-        const int b = thighest(Ja);                  // dimer {a,b}
+        const bool dim1 = Ja != 0;
+        const int b = dim1 ? thighest(Ja) : a;
         const W bb = tbit<W>(b);
-        const W Jb = J.get(b) & E & ~bb;
-        const W rest = E & ~(ba | bb);
-        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
-        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
-        const W Jar = Ja & rest, Jbr = Jb & rest;
-        BG_WORK(dimers, 1);
-        t_xor2(J, Jar, Jbr, Jbr, Jar);                                  // J_c ^= [J_ca] J_b ^ [J_cb] J_a
-        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
-        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
-        E = rest;
+        const W rest1 = E & ~(ba | bb);
+        const W M1 = Ja & rest1;
+        const W M2 = dim1 ? (J.get(b) & rest1) : (W)0;
+        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
+        t_step_scalars<W>(D2, Js, ba, bb, true, dim1, M1, M2, cnt, neg0, neg1, z0, z1);
+        const bool stop1 = z0 && (z1 || !has_s);                        // the whole sum is zero
+        // ---- step 2 on what is left
+        const W left = stop1 ? (W)0 : rest1;
+        const bool on2 = left != 0;
+        const int a2 = on2 ? thighest(left) : a;
+        const W ba2 = on2 ? tbit<W>(a2) : (W)0;
+        const W ra = J.get(a2) ^ ((M1 & ba2) ? M2 : (W)0) ^ ((M2 & ba2) ? M1 : (W)0);
+        const W Ja2 = ra & left & ~ba2;
+        const bool dim2 = Ja2 != 0;
+        const int b2 = dim2 ? thighest(Ja2) : a2;
+        const W bb2 = on2 ? tbit<W>(b2) : (W)0;
+        const W rb = J.get(b2) ^ ((M1 & bb2) ? M2 : (W)0) ^ ((M2 & bb2) ? M1 : (W)0);
+        const W rest2 = left & ~(ba2 | bb2);
+        const W M3 = Ja2 & rest2;
+        const W M4 = dim2 ? (rb & rest2) : (W)0;
+        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (on2 && !dim2) ? 1 : 0);
+        t_step_scalars<W>(D2, Js, ba2, bb2, on2, dim2, M3, M4, cnt, neg0, neg1, z0, z1);
+        // ---- both updates on the rows that stay:  J_c ^= [J_ca] J_b ^ [J_cb] J_a, twice
+        t_xor4(J, M1 & rest2, M2, M2 & rest2, M1, M3, M4, M4, M3);
+        E = (z0 && (z1 || !has_s)) ? (W)0 : rest2;
     }
+}
+
+// ---- the same two-step rounds for 64-bit words, written on 32-bit halves ----------------------------
+// (t > 32.)  The generic version above is correct for uint64_t too, but every 64-bit test / select / shift
+// costs the compiler two or three instructions; here a variable is (bit as two halves, index, row
+// address), bits of D2 / Js are taken with ONE funnel shift and kept as "bit 0 of a word" (upper bits are
+// junk until the end), conditional xors are predicated.
+struct TIdx {
+    uint32_t bl, bh;       // the variable's bit, low and high half
+    uint32_t idx;          // 0..63
+    uint32_t addr;         // device: shared-memory address of its row
+};
+BG_HD TIdx t_top64(uint32_t xl, uint32_t xh, const Rows<uint64_t>& J) {      // highest variable of (xh:xl) != 0
+    TIdx r;
+    const bool ph = xh != 0u;
+    const uint32_t c = (uint32_t)thighest(ph ? xh : xl);
+    const uint32_t bm = 1u << c;
+    r.bl = ph ? 0u : bm; r.bh = ph ? bm : 0u;
+    r.idx = c + (ph ? 32u : 0u);
+    r.addr = c * J.sstride + (ph ? J.sbase + 32u * J.sstride : J.sbase);
+    return r;
+}
+BG_HD void t_ld64(const Rows<uint64_t>& J, const TIdx& i, uint32_t& l, uint32_t& h) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(h) : "r"(i.addr));
+#else
+    const uint64_t v = J.get((int)i.idx); l = (uint32_t)v; h = (uint32_t)(v >> 32);
+#endif
+}
+BG_HD uint32_t t_bit64(uint32_t l, uint32_t h, uint32_t idx) {             // bit idx of (h:l) -> bit 0 (rest: junk)
+    return (uint32_t)((((uint64_t)h << 32) | l) >> idx);
+}
+BG_HD void t_cxor64(uint32_t& l, uint32_t& h, uint32_t c, uint32_t vl, uint32_t vh) {    // (h:l) ^= (vh:vl) if c & 1
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, 1;\n\tsetp.ne.u32 p, t, 0;\n\t"
+        "@p xor.b32 %0, %0, %3;\n\t@p xor.b32 %1, %1, %4;\n\t}" : "+r"(l), "+r"(h) : "r"(c), "r"(vl), "r"(vh));
+#else
+    if (c & 1u) { l ^= vl; h ^= vh; }
+#endif
+}
+// bookkeeping of one step (cf. t_step_scalars): on = 0/1, onm / dm = all-ones masks for "step exists" / "dimer"
+BG_HD void t_step_scalars64(uint32_t& D2l, uint32_t& D2h, uint32_t& Jsl, uint32_t& Jsh, uint32_t ia, uint32_t ib,
+                            uint32_t on, uint32_t onm, uint32_t dm, uint32_t M1l, uint32_t M1h, uint32_t M2l, uint32_t M2h,
+                            uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1) {
+    const uint32_t d2a = t_bit64(D2l, D2h, ia), sa = t_bit64(Jsl, Jsh, ia);
+    const uint32_t d2b = t_bit64(D2l, D2h, ib), sb = t_bit64(Jsl, Jsh, ib);
+    const uint32_t ta = d2a ^ sa;
+    cnt += on;
+    neg0 ^= d2a & d2b & dm;
+    neg1 ^= ta & (d2b ^ sb) & dm;
+    z0 |= d2a & ~dm & onm;
+    z1 |= ta & ~dm & onm;
+    t_cxor64(D2l, D2h, d2b, M1l, M1h);
+    t_cxor64(D2l, D2h, d2a, M2l, M2h);
+    D2l ^= M1l & M2l; D2h ^= M1h & M2h;
+    t_cxor64(Jsl, Jsh, sb, M1l, M1h);
+    t_cxor64(Jsl, Jsh, sa, M2l, M2h);
+}
+BG_HD uint64_t t_mk64(uint32_t l, uint32_t h) { return ((uint64_t)h << 32) | l; }
+
+BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t& Js, uint32_t& cnt, uint32_t& neg0,
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s) {
+    uint32_t El = (uint32_t)E, Eh = (uint32_t)(E >> 32);
+    uint32_t D2l = (uint32_t)D2, D2h = (uint32_t)(D2 >> 32), Jsl = (uint32_t)Js, Jsh = (uint32_t)(Js >> 32);
+    const uint32_t ns = has_s ? 0u : 1u;
+    while ((El | Eh) != 0u) {
+        // ---- step 1: a = highest variable left, b = its highest neighbour (a itself: monomer)
+        const TIdx a = t_top64(El, Eh, J);
+        uint32_t ral, rah;
+        t_ld64(J, a, ral, rah);
+        const uint32_t Jal = ral & El & ~a.bl, Jah = rah & Eh & ~a.bh;
+        const bool dim1 = (Jal | Jah) != 0u;
+        const uint32_t dm1 = dim1 ? ~0u : 0u;
+        const TIdx b = t_top64(dim1 ? Jal : a.bl, dim1 ? Jah : a.bh, J);
+        uint32_t rbl, rbh;
+        t_ld64(J, b, rbl, rbh);
+        const uint32_t r1l = El & ~(a.bl | b.bl), r1h = Eh & ~(a.bh | b.bh);
+        const uint32_t M1l = Jal & r1l, M1h = Jah & r1h;
+        const uint32_t M2l = rbl & r1l & dm1, M2h = rbh & r1h & dm1;
+        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
+        t_step_scalars64(D2l, D2h, Jsl, Jsh, a.idx, b.idx, 1u, ~0u, dm1, M1l, M1h, M2l, M2h, cnt, neg0, neg1, z0, z1);
+        // ---- step 2 on what is left (nothing, if the sum is already known to vanish)
+        const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & ((r1l | r1h) != 0u);
+        const uint32_t ll = go2 ? r1l : 0u, lh = go2 ? r1h : 0u;
+        const TIdx a2 = t_top64(go2 ? r1l : a.bl, go2 ? r1h : a.bh, J);
+        uint32_t ql, qh;
+        t_ld64(J, a2, ql, qh);
+        t_cxor64(ql, qh, t_bit64(M1l, M1h, a2.idx), M2l, M2h);              // row a2 brought up to date with step 1
+        t_cxor64(ql, qh, t_bit64(M2l, M2h, a2.idx), M1l, M1h);
+        const uint32_t Kal = ql & ll & ~a2.bl, Kah = qh & lh & ~a2.bh;
+        const bool dim2 = (Kal | Kah) != 0u;
+        const uint32_t dm2 = dim2 ? ~0u : 0u;
+        const TIdx b2 = t_top64(dim2 ? Kal : a2.bl, dim2 ? Kah : a2.bh, J);
+        uint32_t sl, sh;
+        t_ld64(J, b2, sl, sh);
+        t_cxor64(sl, sh, t_bit64(M1l, M1h, b2.idx), M2l, M2h);
+        t_cxor64(sl, sh, t_bit64(M2l, M2h, b2.idx), M1l, M1h);
+        const uint32_t r2l = ll & ~(a2.bl | b2.bl), r2h = lh & ~(a2.bh | b2.bh);
+        const uint32_t M3l = Kal & r2l, M3h = Kah & r2h;
+        const uint32_t M4l = sl & r2l & dm2, M4h = sh & r2h & dm2;
+        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
+        t_step_scalars64(D2l, D2h, Jsl, Jsh, a2.idx, b2.idx, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3l, M3h, M4l, M4h,
+                         cnt, neg0, neg1, z0, z1);
+        // ---- both updates on the rows that stay
+        t_xor4(J, t_mk64(M1l & r2l, M1h & r2h), t_mk64(M2l, M2h), t_mk64(M2l & r2l, M2h & r2h), t_mk64(M1l, M1h),
+               t_mk64(M3l, M3h), t_mk64(M4l, M4h), t_mk64(M4l, M4h), t_mk64(M3l, M3h));
+        const bool stop = (z0 & (z1 | ns) & 1u) != 0u;
+        El = stop ? 0u : r2l; Eh = stop ? 0u : r2h;
+    }
+    neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
+    E = 0; D2 = t_mk64(D2l, D2h); Js = t_mk64(Jsl, Jsh);
 }
 
 // sum over F_2^A of e^{i pi q/4}    (bg_device.cuh: expsum)
@@ -255,7 +493,7 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     // (Measured and rejected: finishing the variables >= 32 first and then continuing with 32-bit words
     // on the low halves — fewer instructions per lane, but the extra reconvergence point costs more
     // than it saves: 4.83 vs 4.67 ms at t = 40.)
-    t_rounds<W, false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
+    t_rounds(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
     p = 2 * (int)cnt;
     const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
     if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; return; }
@@ -337,12 +575,36 @@ BG_HD bool t_constraints_many(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, 
     return true;
 }
 
+// the thread's working copy of the ambient J.  Device: the warp's ambient rows are 16-byte aligned
+// (k_pairs_tpp pads them), so they are read with 128-bit broadcast loads.
+template <typename W>
+BG_HD void t_copy_in(const Rows<W>& J, const TShared<W>& sh) {
+    const int t = sh.t;
+#if defined(__CUDA_ARCH__)
+    const uint32_t amb = (uint32_t)__cvta_generic_to_shared(sh.J);
+    constexpr int PER = 16 / (int)sizeof(W);
+    int q = 0;
+#pragma unroll 4
+    for (; q + PER <= t; q += PER) {
+        uint32_t x0, x1, x2, x3;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(amb + (uint32_t)q * (uint32_t)sizeof(W)));
+        if (sizeof(W) == 8) {
+            J.put(q, (W)(((uint64_t)x1 << 32) | x0)); J.put(q + 1, (W)(((uint64_t)x3 << 32) | x2));
+        } else {
+            J.put(q, (W)x0); J.put(q + 1, (W)x1); J.put(q + 2, (W)x2); J.put(q + 3, (W)x3);
+        }
+    }
+    for (; q < t; q++) J.put(q, sh.J[q]);
+#else
+    for (int q = 0; q < t; q++) J.put(q, sh.J[q]);
+#endif
+}
+
 // <phi|theta> for a |L> term (prepL): |+> on supp(xt), |0> elsewhere.
 template <typename W, bool MANYC = false>
 BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
     const int t = sh.t;
-#pragma unroll 8
-    for (int q = 0; q < t; q++) J.put(q, sh.J[q]);
+    t_copy_in<W>(J, sh);
     TF<W> f;
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
     f.A = xt & tlowmask<W>(t);

@@ -33,6 +33,7 @@
 
 #include <condition_variable>
 #include <mutex>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -103,14 +104,18 @@ static void random_L(int k, int t, std::vector<uint64_t>& rows) {
     }
 }
 
+// Z(L)'s weight histogram on the device (bg_decomposition_weights); returns "" on success
+typedef std::function<std::string(int t, const std::vector<uint64_t>& L, uint64_t hist[65])> WeightFn;
+
 // decompose (libcirc/probability.c:307-415): choose |H^t> (exact) or |L> with a random k x t L.
-static void decompose(Config& c, std::vector<uint64_t>& L, double* norm, FILE* out) {
+// Returns "" or an error string (only the device histogram of the fidelity loop can fail).
+static std::string decompose(Config& c, std::vector<uint64_t>& L, double* norm, FILE* out, const WeightFn& weights) {
     const int t = c.t;
-    if (t == 0) { c.exact = 0; *norm = 1; return; }
+    if (t == 0) { c.exact = 0; *norm = 1; return ""; }
     const double v = cos(M_PI / 8);
     *norm = pow(2, floor((float)t / 2) / 2);
     if (t % 2) *norm *= 2 * v;
-    if (c.exact) return;
+    if (c.exact) return "";
     const bool forceK = c.k > 0;
     if (!forceK) {
         c.k = (int)ceil(1 - 2 * t * log2(v) - log2(c.fidbound));
@@ -119,7 +124,7 @@ static void decompose(Config& c, std::vector<uint64_t>& L, double* norm, FILE* o
     if (c.k > t / 2 && !forceK && !c.forceL) {
         if (c.verbose) fprintf(out, "k > t/2. Reverting to exact decomposition.\n");
         c.exact = 1;
-        return;
+        return "";
     }
     if (c.k > t) {
         if (forceK && !c.quiet) fprintf(out, "Can't have k > t. Setting k to %d.\n", t);
@@ -133,21 +138,23 @@ static void decompose(Config& c, std::vector<uint64_t>& L, double* norm, FILE* o
             continue;
         }
         if (!c.fidelity) break;
-        // Z(L) = sum_x 2^{-|x|/2} over the 2^k combinations of rows; the reference evaluates
-        // pow(2, -hamming/2) with INTEGER division (probability.c:389), kept as is.
+        // Z(L) = sum_x 2^{-|x|/2} over the 2^k combinations of rows (probability.c:373-391).  The 2^k
+        // Hamming weights are counted on the device; the reference evaluates pow(2, -hamming/2) with
+        // INTEGER division (:389), kept as is.  Every term is a power of two >= 2^-(t/2) and the sum stays
+        // below 2^k, so whenever k + t/2 <= 53 every partial sum is exact in fp64 and the order of
+        // summation is immaterial: the same bits as the reference's loop over i.
+        uint64_t hist[65];
+        const std::string werr = weights(t, L, hist);
+        if (!werr.empty()) return werr;
         Z_L = 0;
-        for (uint64_t i = 0; i < (1ull << c.k); i++) {
-            uint64_t x = 0;
-            for (int j = 0; j < c.k; j++) if ((i >> (c.k - 1 - j)) & 1) x ^= L[j];
-            const int hamming = __builtin_popcountll(x);
-            Z_L += pow(2, -hamming / 2);
-        }
+        for (int w = 64; w >= 0; w--) Z_L += (double)hist[w] * pow(2, -w / 2);
         overlap = pow(2, c.k) * pow(v, 2 * t) / Z_L;
         if (forceK) { fprintf(out, "delta = 1 - <H^t|L>: %lf\n", 1 - overlap); break; }
         if (overlap < 1 - c.fidbound) { if (!c.quiet) fprintf(out, "delta = 1 - <H^t|L>: %lf - Not good enough!\n", 1 - overlap); }
         else if (!c.quiet) fprintf(out, "delta = 1 - <H^t|L>: %lf\n", 1 - overlap);
     }
     if (c.fidelity) *norm = sqrt(pow(2, c.k) * Z_L);
+    return "";
 }
 
 static uint64_t splitmix64(uint64_t x) {
@@ -158,6 +165,9 @@ static uint64_t splitmix64(uint64_t x) {
 }
 
 struct Job {
+    enum Kind { EVALUATE = 0, WEIGHTS = 1 };
+    Kind kind = EVALUATE;
+    uint64_t hist[65];              // WEIGHTS: out
     Config c; std::vector<uint64_t> L; double norm; bg_projector G, H; uint64_t seed;
     double numerator = 0, denominator = 0;
     std::string error;
@@ -224,7 +234,10 @@ private:
             }
             std::string jerr = err;
             double num = 0, den = 0;
-            if (jerr.empty()) {
+            if (jerr.empty() && job->kind == Job::WEIGHTS) {       // decompose()'s fidelity loop: one GPU is plenty
+                if (rank == 0 && bg_decomposition_weights(ctx, job->c.t, (int)job->L.size(), job->L.data(), job->hist))
+                    jerr = bg_last_error(ctx);
+            } else if (jerr.empty()) {
                 const Config& c = job->c;
                 int rc = bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data());
                 if (!rc) {
@@ -305,7 +318,18 @@ static void process(Job& job, FILE* out, Engine& engine, bool chatter, uint64_t 
     if (chatter) fprintf(out, "samples: %d bins: %d t: %d k: %d exact: %d noapprox: %d\n", c.samples, c.bins, c.t, c.k, c.exact, c.noapprox);
     if (c.t > BG_MAX_T) { fprintf(out, "Error: t = %d exceeds the 64-qubit limit of the packed layout.\n", c.t); return; }
 
-    decompose(c, job.L, &job.norm, out);
+    const WeightFn weights = [&](int t, const std::vector<uint64_t>& L, uint64_t hist[65]) -> std::string {
+        std::string err = engine.start();
+        if (!err.empty()) return err;
+        Job wj;
+        wj.kind = Job::WEIGHTS; wj.c.t = t; wj.L = L;
+        engine.run(&wj);
+        if (!wj.error.empty()) return wj.error;
+        memcpy(hist, wj.hist, sizeof wj.hist);
+        return "";
+    };
+    const std::string derr = decompose(c, job.L, &job.norm, out, weights);
+    if (!derr.empty()) { fprintf(out, "Error: %s\n", derr.c_str()); return; }
     if (c.verbose) {
         if (c.exact) fprintf(out, "Using exact decomposition of |H^t>: 2^%d\n", (c.t + 1) / 2);
         else fprintf(out, "Stabilizer rank of |L>: 2^%d\n", c.k);

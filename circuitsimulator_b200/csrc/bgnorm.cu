@@ -34,6 +34,10 @@
 
 using namespace bg;
 
+#ifndef BG_TPP_MAX_THREADS
+#define BG_TPP_MAX_THREADS 128          // largest CTA of k_pairs_tpp (BG_TPP_WARPS * 32)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // device-side records
 // ------------------------------------------------------------------------------------------
@@ -286,15 +290,18 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
     return (long long)(((unsigned long long)hi << 32) | lo);
 }
 
+// ambient rows per warp (+ the check rows when MANYC), padded to a multiple of 4 words: 16-byte aligned
+__host__ __device__ __forceinline__ int tpp_amb_rows(int t, bool manyc) { return ((manyc ? 2 * t : t) + 3) & ~3; }
+
 template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
-__global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
+__global__ void __launch_bounds__(BG_TPP_MAX_THREADS) k_pairs_tpp(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     const int lane = bg_lane(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int t = a.t;
     if (MANYC && *a.n_warp_routed == 0ull) return;      // nothing has more than TPP_MAXC parity checks
     // per warp: t ambient rows (+ t check rows when MANYC); per thread: t working rows (+ t history rows)
-    const int amb_rows = MANYC ? 2 * t : t;
+    const int amb_rows = tpp_amb_rows(t, MANYC);
     uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
     W* s_amb = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + warp * amb_rows;
     W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * amb_rows + threadIdx.x;
@@ -358,11 +365,13 @@ __global__ void __launch_bounds__(128) k_pairs_tpp(PairArgs a) {
             const int i = g + lane;
             const int nat = (i < i1 && (TRI || a.epm)) ? a.term_nat[i] : i;
             if (i < i1 && !(TRI && nat < diag_index)) {
+                const unsigned group = __activemask();
                 const W term = (W)terms[i];
                 int e, p, m;
                 if (EXACT) t_term_H<W, MANYC>(rows, sh, term, e, p, m);
                 else if (LAZY && use_lazy) t_term_L_lazy<W>(rows, sh, term, e, p, m);
                 else t_term_L<W, MANYC>(rows, sh, term, e, p, m);
+                __syncwarp(group);          // the lanes leave the elimination at different times: accumulate together
                 if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
                 else zw_add(z, e, p, m, sh_);
                 if (a.epm) {
@@ -677,7 +686,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e6 = getenv("BG_LAZY")) ctx->lazy = atoi(e6) != 0;
-    if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= 4) ctx->tpp_warps = v; }
+    if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= BG_TPP_MAX_THREADS / 32) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
     *out = ctx;
@@ -926,6 +935,12 @@ template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
 static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent grid: exactly the CTAs that are resident at once (a multiple of the SM count), fewer if
+    // there are not that many work items
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY>, 32 * ctx->tpp_warps, smem));
+    if (per_sm < 1) return fail(ctx, "k_pairs_tpp: a CTA of %d warps with %zu bytes of shared memory does not fit an SM", ctx->tpp_warps, smem);
+    blocks = std::min(blocks, ctx->sm_count * per_sm);
     k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
@@ -972,17 +987,17 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;
         const int tw = ctx->tpp_warps;
-        long long tb = (long long)ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK / tw;
+        long long tb = (long long)ctx->sm_count * 64;            // capped to the resident CTAs in launch_tpp_inst
         const long long tneed = (long long)((items + tw - 1) / tw);
         if (tb > tneed) tb = tneed;
         if (tb < 1) tb = 1;
         // samples with <= TPP_MAXC parity checks, then (returns at once if there are none) the rest
         a.counter = cnt;
-        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb;
+        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, false) * wb + (size_t)a.t * 32 * tw * wb;
         if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
         else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
         a.counter = cnt + 3;
-        smem = (size_t)a.smem_terms * 8 + 2 * ((size_t)tw * a.t * wb + (size_t)a.t * 32 * tw * wb);
+        smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, true) * wb + 2 * (size_t)a.t * 32 * tw * wb;
         if (a.t <= 32) return launch_tpp_w<uint32_t, true>(ctx, a, (int)tb, smem);
         return launch_tpp_w<uint64_t, true>(ctx, a, (int)tb, smem);
     }
@@ -1572,6 +1587,75 @@ extern "C" int bg_measure_int_peak(bg_ctx* ctx, double* lop3_lane_ops_per_s, dou
     cudaFree(sink);
     if (lop3_lane_ops_per_s) *lop3_lane_ops_per_s = res[0];
     if (popc_lane_ops_per_s) *popc_lane_ops_per_s = res[1];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// decompose()'s fidelity loop (libcirc/probability.c:373-391): the Hamming weights of all 2^k
+// combinations of the rows of L.  Thread g owns the 2^low combinations whose high bits are g and walks
+// them in Gray-code order (one XOR + one POPC per combination); counts go to lane-private columns of a
+// per-warp histogram in shared memory (bank = lane, no atomics), flushed with one atomic per bin.
+// ------------------------------------------------------------------------------------------
+#define WH_WARPS 4
+__global__ void __launch_bounds__(32 * WH_WARPS) k_weight_hist(const uint64_t* __restrict__ L, int k, int low,
+                                                               unsigned long long* hist) {
+    __shared__ uint32_t s_h[WH_WARPS][65][32];
+    __shared__ uint64_t s_L[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) s_L[j] = j < k ? L[j] : 0ull;
+    for (int j = lane; j < 65 * 32; j += 32) (&s_h[warp][0][0])[j] = 0u;
+    __syncthreads();
+    const unsigned long long groups = 1ull << (k - low);
+    const unsigned long long per = 1ull << low;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (unsigned long long)gridDim.x * blockDim.x) {
+        uint64_t x = 0;
+        for (int j = low; j < k; j++) if ((g >> (j - low)) & 1ull) x ^= s_L[j];
+        s_h[warp][__popcll(x)][lane]++;
+        for (unsigned long long c = 1; c < per; c++) {
+            x ^= s_L[__ffsll((long long)c) - 1];          // Gray code: step c flips bit ctz(c)
+            s_h[warp][__popcll(x)][lane]++;
+        }
+    }
+    __syncwarp();
+    for (int w = lane; w < 65; w += 32) {
+        unsigned long long sum = 0;
+        for (int l = 0; l < 32; l++) sum += s_h[warp][w][l];
+        if (sum) atomicAdd(&hist[w], sum);
+    }
+}
+
+extern "C" int bg_decomposition_weights(bg_ctx* ctx, int t, int k, const uint64_t* L_rows, uint64_t hist[65]) {
+    if (!ctx) return fail(nullptr, "bg_decomposition_weights: null ctx");
+    if (!hist) return fail(ctx, "bg_decomposition_weights: null hist");
+    if (t < 1 || t > BG_MAX_T) return fail(ctx, "bg_decomposition_weights: t = %d outside 1..%d", t, BG_MAX_T);
+    if (k < 0 || k > t || k > 44) return fail(ctx, "bg_decomposition_weights: k = %d outside 0..min(t,44)", k);
+    if (k > 0 && !L_rows) return fail(ctx, "bg_decomposition_weights: L_rows is null");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t maskt = t >= 64 ? ~0ull : ((1ull << t) - 1);
+    uint64_t rows[64];
+    for (int j = 0; j < 64; j++) rows[j] = j < k ? (L_rows[j] & maskt) : 0ull;
+    unsigned long long* d = nullptr;                 // [0..64] histogram, [65..128] the rows
+    CK(cudaMalloc((void**)&d, (65 + 64) * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, 65 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 65, rows, sizeof rows, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        // every thread walks 2^low combinations per group, low <= 16, with 2^18 groups (more than the
+        // resident threads) as soon as k allows; a lane-private counter stays far below 2^32 for k <= 44
+        const int low = std::min(16, std::max(0, k - 18));
+        const unsigned long long groups = 1ull << (k - low);
+        const int threads = 32 * WH_WARPS;
+        const int blocks = (int)std::min<unsigned long long>((groups + threads - 1) / threads, (unsigned long long)ctx->sm_count * 8);
+        k_weight_hist<<<blocks, threads, 0, ctx->stream>>>((const uint64_t*)(d + 65), k, low, d);
+        e = cudaGetLastError();
+    }
+    unsigned long long h[65];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, "bg_decomposition_weights: %s", cudaGetErrorString(e));
+    for (int w = 0; w < 65; w++) hist[w] = h[w];
+    ctx->stats.launches = 1; ctx->stats.h2d_bytes = sizeof rows; ctx->stats.d2h_bytes = sizeof h;
     return 0;
 }
 

@@ -104,6 +104,14 @@ int  bg_projector_from_bitmatrix(bg_projector* out, int nstabs, int nqubits,
                                  const uint8_t* phase_sign, const uint8_t* phase_complex,
                                  const uint8_t* xs, const uint8_t* zs);
 
+/* decompose()'s fidelity loop (libcirc/probability.c:373-391), which the
+ * reference runs on the host over all 2^k combinations of the rows of L:
+ * hist[w] = #{ i < 2^k : |x~_i| = w }, w = 0..64, x~_i as in prepL.  From it
+ * Z(L) = sum_w hist[w] * 2^-(w/2) (INTEGER w/2, as the reference's
+ * pow(2, -hamming/2) evaluates) and <H^t|L> = 2^k cos(pi/8)^2t / Z(L).  Does
+ * not touch the context's current decomposition. */
+int  bg_decomposition_weights(bg_ctx* ctx, int t, int k, const uint64_t* L_rows, uint64_t hist[65]);
+
 /* ---- the hot path ------------------------------------------------------ */
 
 /* Replaces multiSampledProjector/sampledProjector/singleProjectorSample

@@ -234,6 +234,8 @@ class Oracle(_Api):
         lib.orc_Lbits.restype = C.c_uint64
         lib.orc_wordops.restype = C.c_uint64
         lib.orc_identity_state.argtypes = [_P(State), C.c_int, C.c_int]
+        lib.orc_decompose_ZL.argtypes = [C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_uint64)]
+        lib.orc_decompose_ZL.restype = C.c_double
         self.libc = C.CDLL(None)
 
     def srand(self, seed):
@@ -277,6 +279,12 @@ class Oracle(_Api):
     def sampled_projector_libc(self, P, exact, Lrows, norm, samples):
         return self.lib.orc_sampled_projector_libc(C.byref(P), int(bool(exact)), 0 if exact else len(Lrows),
                                                    u64_array(Lrows or []), norm, samples)
+
+    def decompose_ZL(self, t, Lrows):
+        """(Z(L), weight histogram) of decompose()'s fidelity loop."""
+        hist = (C.c_uint64 * 65)()
+        z = self.lib.orc_decompose_ZL(t, len(Lrows), u64_array(Lrows), hist)
+        return z, [int(v) for v in hist]
 
     def wordops(self, reset=False):
         v = self.lib.orc_wordops()

@@ -698,5 +698,23 @@ double orc_exact_projector(const bg_projector* P, int exact, int k, const uint64
     return sqrt(tr * tr + ti * ti);
 }
 
+/* decompose()'s fidelity loop — probability.c:373-391.  Z(L) = sum over the 2^k combinations of
+ * the rows of L of pow(2, -hamming/2): `hamming/2` is an INTEGER division in the reference (both
+ * operands are ints), kept as is.  Also returns the weight histogram the CUDA path produces.
+ * hist may be NULL. */
+double orc_decompose_ZL(int t, int k, const uint64_t* Lrows, uint64_t* hist) {
+    double Z_L = 0;
+    if (hist) memset(hist, 0, 65 * sizeof(uint64_t));
+    for (uint64_t i = 0; i < (1ull << k); i++) {
+        uint64_t x = 0;
+        for (int j = 0; j < k; j++) if ((i >> (k - 1 - j)) & 1ull) x ^= Lrows[j];     /* binrep is MSB-first */
+        int hamming = 0;
+        for (int q = 0; q < t; q++) hamming += bit(x, q);
+        if (hist) hist[hamming]++;
+        Z_L += pow(2, -hamming / 2);
+    }
+    return Z_L;
+}
+
 size_t orc_sizeof_state(void) { return sizeof(bg_state); }
 size_t orc_sizeof_projector(void) { return sizeof(bg_projector); }

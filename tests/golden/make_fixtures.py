@@ -7,6 +7,7 @@ The GPU box has neither: tests read the committed outputs of this script.
     python tests/golden/make_fixtures.py streams     # back-end instruction streams (main.py file=)
     python tests/golden/make_fixtures.py refpairs    # pairs + (eps,p,m) from the compiled reference
     python tests/golden/make_fixtures.py samples     # theta / projected theta / per-pair epm / values
+    python tests/golden/make_fixtures.py fidelity    # decompose()'s -fidelity loop through the compiled reference
     python tests/golden/make_fixtures.py all
 
 What is read from the reference (data, never source code):
@@ -427,6 +428,40 @@ def samples():
         print(name, "samples", len(rec["value"]), "alive", int(np.sum(rec["alive"])))
 
 
+def fidelity():
+    """decompose() with fidelity = 1 (libcirc/probability.c:361-410) through the COMPILED reference back end
+    (oracle/_ref/mpibackend_ref): for an empty projector H the printed denominator is norm^2 = 2^k Z(L)
+    (innerprod.c:47; G is empty too, so nothing is sampled), and the chatter line carries delta = 1 - <H^t|L>.  L comes from libc rand() in its
+    default state (decompose runs before srand, probability.c:153,182), so it is reproducible: the fixture
+    stores L as BitMatrixSetRandom (utils/matrix.c:301-306) lays it out."""
+    import ctypes
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "mpibackend_ref")
+    libc = ctypes.CDLL(None)
+    cases = []
+    for (t, k) in [(4, 2), (12, 5), (16, 8), (33, 7), (40, 9), (40, 12), (60, 10), (64, 11)]:
+        tok = [0, 0, 0, 1, 1, t, k, 0, 1e-05, 1, 0, 1, 1]            # fidelity = 1, forceL, forceSample
+        tok += [0, 0, 0, 0]                                           # G = H = empty -> norm^2, no sampling at all
+        out = subprocess.run([exe, "stdin"], input="\n".join(str(v) for v in tok) + "\n", capture_output=True,
+                             text=True, check=True).stdout.split("\n")
+        lines = [ln for ln in out if ln.strip()]
+        delta = [float(re.search(r"delta = 1 - <H\^t\|L>: ([-0-9.eE]+)", ln).group(1)) for ln in lines if "delta" in ln]
+        libc.srand(1)
+        rows = [0] * k
+        for b in range((k * t + 7) // 8):
+            byte = libc.rand() % 256
+            for j in range(8):
+                loc = 8 * b + j
+                if loc < k * t and (byte >> (7 - j)) & 1:
+                    rows[loc // t] |= 1 << (loc % t)
+        cases.append({"t": t, "k": k, "L_rows": [str(r) for r in rows], "delta_printed": delta[-1],
+                      "numerator": lines[-2], "denominator": lines[-1]})
+        print("fidelity t=%d k=%d norm^2=%s delta=%g" % (t, k, lines[-1], delta[-1]))
+    with open(os.path.join(HERE, "ref_fidelity.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_fixtures.py fidelity", "cases": cases}, f, indent=1)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("kats", "all"):
@@ -437,3 +472,5 @@ if __name__ == "__main__":
         refpairs()
     if what in ("samples", "all"):
         samples()
+    if what in ("fidelity", "all"):
+        fidelity()

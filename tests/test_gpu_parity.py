@@ -501,3 +501,42 @@ def test_device_rng_law(be, oracle):
             offdiag += bit_ab.sum()
         assert np.array_equal((J[:, a] >> np.uint64(a)) & np.uint64(1), (D1full >> np.uint64(a)) & np.uint64(1))
     assert abs(offdiag / (len(full) * t * (t - 1) / 2) - 0.5) < 0.01
+
+
+def _fidelity_cases():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "ref_fidelity.json")))["cases"]
+
+
+def test_decomposition_weights_vs_oracle(be, oracle):
+    """decompose()'s fidelity loop (libcirc/probability.c:373-391) on the device: the weight histogram of the
+    2^k combinations of L's rows, bit for bit against the oracle's restatement of that loop — on the L matrices
+    the compiled reference drew (tests/golden/ref_fidelity.json) and on edge cases (k = 0, 1, t = 64, a k large
+    enough for every thread to walk a Gray-code run)."""
+    cases = [(c["t"], [int(r) for r in c["L_rows"]]) for c in _fidelity_cases()]
+    rs = np.random.RandomState(11)
+    cases += [(5, []), (1, [1]), (64, [int(rs.randint(0, 2 ** 62)) | (1 << 63)]),
+              (64, [int(rs.randint(0, 2 ** 62)) * 4 + int(rs.randint(0, 4)) for _ in range(16)]),
+              (47, [int(rs.randint(0, 2 ** 47)) for _ in range(21)]),
+              (9, [0, 0, 5])]                                   # rank-deficient L: combinations repeat
+    for t, rows in cases:
+        want_z, want_hist = oracle.decompose_ZL(t, [r & ((1 << t) - 1) for r in rows])
+        got = be.decomposition_weights(t, rows)
+        assert got == want_hist, (t, len(rows))
+        assert sum(got) == 1 << len(rows)
+        z = sum(float(h) * 2.0 ** (-(w // 2)) for w, h in enumerate(got))
+        assert z == want_z, (t, len(rows), z, want_z)
+
+
+def test_backend_fidelity_option_matches_compiled_reference():
+    """The drop-in executable with fidelity = 1: same L from libc rand(), Z(L) from the device histogram; for
+    empty projectors the two printed lines are norm^2 = 2^k Z(L) (innerprod.c:47) — the same 17 digits as the
+    compiled reference printed — and the chatter carries the same delta."""
+    import re
+    import circuitsimulator_b200 as bg
+    for c in _fidelity_cases():
+        tok = [0, 0, 0, 1, 1, c["t"], c["k"], 0, 1e-05, 1, 0, 1, 1, 0, 0, 0, 0]
+        num, den, lines = bg.run_backend("\n".join(str(v) for v in tok) + "\n", env={"BG_SEED": 1})
+        assert "%.17e" % num == c["numerator"] and "%.17e" % den == c["denominator"], (c["t"], c["k"], lines[-2:])
+        delta = [float(re.search(r"delta = 1 - <H\^t\|L>: ([-0-9.eE]+)", ln).group(1)) for ln in lines if "delta" in ln]
+        assert delta and delta[-1] == c["delta_printed"]
