@@ -555,16 +555,13 @@ BG_DEV void zw_add_pow(Zw& z, int e, long long mag) {
     z.a[3] += (j == 3) ? v : 0;
 }
 BG_DEV void zw_add(Zw& z, int eps, int p, int m, int sh) {
-    if (!eps) return;
-    const int f = (p >= 0 ? p : p - 1) / 2;              // floor(p/2)
-    const long long mag = 1ll << (sh + f);
-    const int mm = m & 7;
-    if ((p & 1) == 0) {
-        zw_add_pow(z, mm, mag);
-    } else {                                             // sqrt2 w^m = w^{m+1} + w^{m-1}
-        zw_add_pow(z, (mm + 1) & 7, mag);
-        zw_add_pow(z, (mm + 7) & 7, mag);
-    }
+    // no branches: the 32 lanes of a warp accumulate together.  eps = 0 adds 0; an odd p adds
+    // sqrt2 w^m = w^{m+1} + w^{m-1}, an even p adds w^m (second term 0).
+    const int f = p >> 1;                                // floor(p/2), also for p < 0
+    const long long mag = eps ? (1ll << ((sh + f) & 63)) : 0ll;
+    const int odd = p & 1, mm = m & 7;
+    zw_add_pow(z, (mm + odd) & 7, mag);
+    zw_add_pow(z, (mm + 7) & 7, odd ? mag : 0ll);
 }
 
 }  // namespace bg

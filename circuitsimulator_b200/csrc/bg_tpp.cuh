@@ -362,6 +362,67 @@ BG_HD void t_rounds(const Rows<W>& J, W& E, W& D2, W& Js, uint32_t& cnt, uint32_
     }
 }
 
+// ---- the same two-step rounds for 32-bit words (t <= 32, and the tail of the 64-bit case) -----------
+// Bits of D2 / Js are taken with one shift and kept as "bit 0 of a word" (upper bits are junk until the
+// end); conditional xors are predicated.
+BG_HD void t_cxor32(uint32_t& x, uint32_t c, uint32_t v) {            // x ^= v if c & 1
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, 1;\n\tsetp.ne.u32 p, t, 0;\n\t@p xor.b32 %0, %0, %2;\n\t}"
+        : "+r"(x) : "r"(c), "r"(v));
+#else
+    if (c & 1u) x ^= v;
+#endif
+}
+BG_HD void t_step_scalars32(uint32_t& D2, uint32_t& Js, uint32_t ia, uint32_t ib, uint32_t on, uint32_t onm, uint32_t dm,
+                            uint32_t M1, uint32_t M2, uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1) {
+    const uint32_t d2a = D2 >> ia, sa = Js >> ia, d2b = D2 >> ib, sb = Js >> ib;      // bit 0; upper bits junk
+    const uint32_t ta = d2a ^ sa;
+    cnt += on;
+    neg0 ^= d2a & d2b & dm;
+    neg1 ^= ta & (d2b ^ sb) & dm;
+    z0 |= d2a & ~dm & onm;
+    z1 |= ta & ~dm & onm;
+    t_cxor32(D2, d2b, M1); t_cxor32(D2, d2a, M2); D2 ^= M1 & M2;
+    t_cxor32(Js, sb, M1); t_cxor32(Js, sa, M2);
+}
+BG_HD void t_rounds(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_t& Js, uint32_t& cnt, uint32_t& neg0,
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s) {
+    const uint32_t ns = has_s ? 0u : 1u;
+    while (E != 0u) {
+        // ---- step 1
+        const uint32_t a = (uint32_t)thighest(E), ba = 1u << a;
+        const uint32_t Ja = J.get((int)a) & E & ~ba;
+        const bool dim1 = Ja != 0u;
+        const uint32_t dm1 = dim1 ? ~0u : 0u;
+        const uint32_t b = (uint32_t)thighest(dim1 ? Ja : ba), bb = 1u << b;
+        const uint32_t r1 = E & ~(ba | bb);
+        const uint32_t M1 = Ja & r1;
+        const uint32_t M2 = J.get((int)b) & r1 & dm1;
+        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
+        t_step_scalars32(D2, Js, a, b, 1u, ~0u, dm1, M1, M2, cnt, neg0, neg1, z0, z1);
+        // ---- step 2
+        const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & (r1 != 0u);
+        const uint32_t left = go2 ? r1 : 0u;
+        const uint32_t a2 = (uint32_t)thighest(go2 ? r1 : ba), ba2 = 1u << a2;
+        uint32_t q = J.get((int)a2);
+        t_cxor32(q, M1 >> a2, M2); t_cxor32(q, M2 >> a2, M1);
+        const uint32_t Ka = q & left & ~ba2;
+        const bool dim2 = Ka != 0u;
+        const uint32_t dm2 = dim2 ? ~0u : 0u;
+        const uint32_t b2 = (uint32_t)thighest(dim2 ? Ka : ba2), bb2 = 1u << b2;
+        uint32_t r = J.get((int)b2);
+        t_cxor32(r, M1 >> b2, M2); t_cxor32(r, M2 >> b2, M1);
+        const uint32_t r2 = left & ~(ba2 | bb2);
+        const uint32_t M3 = Ka & r2;
+        const uint32_t M4 = r & r2 & dm2;
+        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
+        t_step_scalars32(D2, Js, a2, b2, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3, M4, cnt, neg0, neg1, z0, z1);
+        t_xor4(J, M1 & r2, M2, M2 & r2, M1, M3, M4, M4, M3);
+        E = (z0 & (z1 | ns) & 1u) ? 0u : r2;
+    }
+    neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
+}
+
 // ---- the same two-step rounds for 64-bit words, written on 32-bit halves ----------------------------
 // (t > 32.)  The generic version above is correct for uint64_t too, but every 64-bit test / select / shift
 // costs the compiler two or three instructions; here a variable is (bit as two halves, index, row
@@ -426,6 +487,13 @@ BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t
     uint32_t D2l = (uint32_t)D2, D2h = (uint32_t)(D2 >> 32), Jsl = (uint32_t)Js, Jsh = (uint32_t)(Js >> 32);
     const uint32_t ns = has_s ? 0u : 1u;
     while ((El | Eh) != 0u) {
+        // Variables are eliminated from the top, so the high halves die first: once no lane of the warp has
+        // a variable >= 32 left, the rounds continue on the low halves of the same rows with 32-bit code.
+#if defined(__CUDA_ARCH__)
+        if (__all_sync(__activemask(), Eh == 0u)) break;
+#else
+        if (Eh == 0u) break;
+#endif
         // ---- step 1: a = highest variable left, b = its highest neighbour (a itself: monomer)
         const TIdx a = t_top64(El, Eh, J);
         uint32_t ral, rah;
@@ -470,6 +538,12 @@ BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t
         El = stop ? 0u : r2l; Eh = stop ? 0u : r2h;
     }
     neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
+    if (El != 0u) {
+        Rows<uint32_t> Jl;                       // the low words of the same rows
+        Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
+        Jl.sbase = J.sbase; Jl.sstride = J.sstride;
+        t_rounds(Jl, El, D2l, Jsl, cnt, neg0, neg1, z0, z1, has_s);
+    }
     E = 0; D2 = t_mk64(D2l, D2h); Js = t_mk64(Jsl, Jsh);
 }
 
