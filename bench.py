@@ -126,7 +126,9 @@ def fixed_L(k, t):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons during the timed region (B200_PROFILING.md recipe).  Reads
+    NVML in-process (the library nvidia-smi itself uses): a query takes microseconds and does not fork, so a
+    timed region of a few tens of ms is not perturbed; falls back to polling the nvidia-smi binary."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -134,17 +136,44 @@ class ClockSampler(threading.Thread):
     def __init__(self, device):
         super().__init__(daemon=True)
         self.device, self.rows, self.stop_flag = device, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+
+        def act(name):
+            bit = getattr(n, name, 0)
+            return "Active" if (r & bit) else "Not Active"
+        return [str(self.device), str(sm), str(mx), "%.1f" % pw, hex(r),
+                act("nvmlClocksEventReasonHwSlowdown"), act("nvmlClocksEventReasonHwThermalSlowdown"),
+                act("nvmlClocksEventReasonSwThermalSlowdown"), act("nvmlClocksEventReasonSwPowerCap")]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                      "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
-                for ln in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in ln.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout
+                    for ln in out.strip().splitlines():
+                        self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            time.sleep(0.3)
+            time.sleep(0.05 if self.nvml is not None else 0.3)
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -156,7 +185,8 @@ class ClockSampler(threading.Thread):
                 if len(r) > 5 + j and r[5 + j].lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -333,15 +363,16 @@ def main():
         step_resident()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, prepare_ms, pairs_ms, launches = 0.0, 0.0, 0.0, 0
+    kernel_ms, prepare_ms, pairs_ms, launches, pair_launches = 0.0, 0.0, 0.0, 0, 0
 
     def account():
-        nonlocal kernel_ms, prepare_ms, pairs_ms, launches
+        nonlocal kernel_ms, prepare_ms, pairs_ms, launches, pair_launches
         st = ctx.stats()
         kernel_ms += st["kernel_ms"]
         prepare_ms += st["prepare_ms"]
         pairs_ms += st["pairs_ms"]
         launches += st["launches"]
+        pair_launches += st["pair_launches"]
 
     # K steps, two in flight: the all-reduce + 16-byte read-back of step i overlap the kernels of
     # step i+1 (every step's result is delivered inside the timed region)
@@ -404,11 +435,15 @@ def main():
         wpath = os.path.join(ROOT, "profiles", "work_model.json")
         wm = json.load(open(wpath)).get(cfgname, {}) if os.path.exists(wpath) else {}
         lane_ops = wm.get("alu_lane_ops_per_pair")           # DESIGN.md "Roofline": algorithmic lane-ops / pair
-        per_launch_pairs = samples * chi / world             # one k_pairs_tpp launch = one projector on this rank
-        k_ms = pairs_ms / max(1, args.steps * 2)             # CUDA events around the pair kernels, per launch
+        # one k_pairs_tpp launch = this rank's samples of BOTH projectors (fused job), CUDA events around it
+        launches_per_step = max(1, pair_launches) / args.steps
+        per_launch_pairs = 2 * samples * chi / world / launches_per_step
+        k_ms = pairs_ms / max(1, pair_launches)
         roof = {"bound": "int_alu", "unit": "Tlaneop/s",
-                "kernel": "k_pairs_tpp", "kernel_ms": k_ms, "kernel_share_of_step": 2 * k_ms / (ms / args.steps),
-                "prepare_ms": prepare_ms / max(1, args.steps * 2),
+                "kernel": "k_pairs_tpp", "kernel_ms": k_ms, "launches_per_step": launches_per_step,
+                "pairs_per_launch": per_launch_pairs,
+                "kernel_share_of_step": launches_per_step * k_ms / (ms / args.steps),
+                "prepare_ms": prepare_ms / max(1, pair_launches),
                 "achieved": (per_launch_pairs * lane_ops / (k_ms * 1e-3) / 1e12) if lane_ops and k_ms > 0 else None,
                 "peak": lop3_peak / 1e12,
                 "peak_source": "LOP3 lane-ops/s measured in this run by bg_measure_int_peak (64 lanes/clk/SM x 148 SMs)",

@@ -62,6 +62,9 @@ struct PrepArgs {
     const bg_projector* P;
     // SRC_RNG
     uint64_t seed; uint32_t bin; uint64_t first, stride;
+    // fused two-projector job (SRC_RNG): records [n_first, n_samples) belong to projector P2 / seed2, sample
+    // index restarting at `first`; n_first = n_samples otherwise
+    int n_first; const bg_projector* P2; uint64_t seed2;
     const double* cdf;
     // SRC_STATES
     const bg_state* states;
@@ -151,13 +154,16 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
     const int nw = gridDim.x * warps_per_block;
     for (int idx = gw; idx < a.n_samples; idx += nw) {
         Native<NS> st;
-        if (SRC == SRC_RNG) native_random<NS>(st, a.t, a.seed, a.bin, a.first + (uint64_t)idx * a.stride, a.cdf);
+        const bool second = SRC == SRC_RNG && idx >= a.n_first;
+        const bg_projector* P = second ? a.P2 : a.P;
+        if (SRC == SRC_RNG) native_random<NS>(st, a.t, second ? a.seed2 : a.seed, a.bin,
+                                              a.first + (uint64_t)(second ? idx - a.n_first : idx) * a.stride, a.cdf);
         else if (SRC == SRC_STATES) native_load<NS>(st, &a.states[idx]);
         else term_native<NS>(st, a.t, a.exact, a.terms[a.first + (uint64_t)idx * a.stride]);
         if (a.raw_out) native_store_raw<NS>(st, &a.raw_out[idx], &a.raw_A[idx]);
         int npf = 0;
         bool alive = true;
-        if (a.project) alive = project_native<NS>(st, a.P, npf);
+        if (a.project) alive = project_native<NS>(st, P, npf);
         SampleRec* r = &a.recs[idx];
         if (lane < 4) {
             if (a.zw) a.zw[(size_t)idx * 4 + lane] = 0;
@@ -462,9 +468,13 @@ __global__ void k_finalize_sampled(const SampleRec* recs, const long long* zw, i
 #define FIN_BLOCKS 32
 __global__ void __launch_bounds__(1024) k_finalize_sum_sampled(const SampleRec* recs, const long long* zw, int n, int t,
                                                                double* per_sample, double* out, double* partials,
-                                                               unsigned int* ticket) {
+                                                               unsigned int* ticket, int out_stride) {
     __shared__ double sh[1024];
     __shared__ bool last;
+    // blockIdx.y = segment: samples [seg * n, (seg + 1) * n) are one projector's (fused two-projector job)
+    const int seg = blockIdx.y;
+    recs += (size_t)seg * n; zw += (size_t)seg * n * 4; per_sample += (size_t)seg * n;
+    out += seg * out_stride; partials += seg * FIN_BLOCKS; ticket += seg;
     const int shf = t / 2 + 1;
     double acc = 0.0;
     for (int i = blockIdx.x * 1024 + threadIdx.x; i < n; i += FIN_BLOCKS * 1024) {
@@ -582,6 +592,7 @@ struct bg_ctx {
     int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (wins at t = 60, loses at t = 40)
     int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
+    int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
     double* d_red = nullptr;                    // [2 slots][8] reduction outputs
@@ -675,17 +686,18 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 16 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_partials, 64 * sizeof(double)) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_ticket, 2 * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cdf, (BG_MAX_T + 1) * sizeof(double)) != cudaSuccess) {
         int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx; return r;
     }
     if (const char* e1 = getenv("BG_CTAS_PER_SM")) { int v = atoi(e1); if (v >= 1 && v <= 16) ctx->ctas_per_sm = v; }
     cudaMemset(ctx->d_red, 0, 16 * sizeof(double));
-    cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
+    cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int));
     cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e6 = getenv("BG_LAZY")) ctx->lazy = atoi(e6) != 0;
+    if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
     if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= BG_TPP_MAX_THREADS / 32) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
@@ -918,6 +930,7 @@ static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
     CK(cudaMemsetAsync(CNT(ctx) + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
     a.force_warp = ctx->force_warp;
+    if (!a.P2) a.n_first = a.n_samples;
     a.n_warp_routed = CNT(ctx) + 4 * ctx->cur + 2;
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
@@ -1055,7 +1068,7 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     }
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
-    if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
+    if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
     for (int j = 0; j < nproj; j++)
         CK(cudaMemcpyAsync(ctx->d_P + j, Ps[j], sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // the caller's projector may be a temporary
@@ -1099,7 +1112,43 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
     CK(rec_event(ctx, EVP(ctx, pj, 2)));
     ctx->phase_events = true;
     k_finalize_sum_sampled<<<FIN_BLOCKS, 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, RED(ctx) + red_slot,
-                                                                  ctx->d_partials, ctx->d_ticket);
+                                                                  ctx->d_partials, ctx->d_ticket, 0);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 1;
+    return 0;
+}
+
+static inline bool fused2(const bg_ctx* ctx) {
+    return ctx->fuse2 && ctx->nproj == 2 && ctx->bins == 1 && shard_count(ctx->samples, ctx->rank, ctx->world) <= (1ull << 29);
+}
+
+// Both projectors of one probability() evaluation (bins = 1) in ONE launch per kernel: the records of
+// G' and H' sit back to back, the terms are the same for both, so the pair kernel sees 2n samples — half
+// the launches and one tail instead of two (what matters when 8 GPUs share the samples).
+static int run_fused2(bg_ctx* ctx) {
+    const uint64_t mine = shard_count(ctx->samples, ctx->rank, ctx->world);
+    const int n = (int)mine;
+    if (n == 0) { CK(cudaMemsetAsync(RED(ctx), 0, 8 * sizeof(double), ctx->stream)); return 0; }
+    ctx->cur = 0;
+    CK(cudaMemsetAsync(CNT(ctx) + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PrepArgs pa; memset(&pa, 0, sizeof pa);
+    pa.recs = ctx->d_recs; pa.n_samples = 2 * n; pa.n_first = n; pa.t = ctx->t; pa.project = 1;
+    pa.P = ctx->d_P; pa.P2 = ctx->d_P + 1; pa.seed = ctx->seeds[0]; pa.seed2 = ctx->seeds[1];
+    pa.bin = 0; pa.first = (uint64_t)ctx->rank; pa.stride = (uint64_t)ctx->world;
+    pa.cdf = ctx->d_cdf;
+    pa.zw = ctx->d_zw;
+    CK(rec_event(ctx, EVP(ctx, 0, 0)));
+    if (launch_prepare(ctx, SRC_RNG, pa)) return 1;
+    CK(rec_event(ctx, EVP(ctx, 0, 1)));
+    PairArgs qa; memset(&qa, 0, sizeof qa);
+    qa.recs = ctx->d_recs; qa.n_samples = 2 * n; qa.terms = ctx->d_terms; qa.nterms = (int)ctx->terms_host.size();
+    qa.t = ctx->t; qa.zw = ctx->d_zw; qa.zw2 = ctx->d_zw2;
+    if (launch_pairs(ctx, qa)) return 1;
+    CK(rec_event(ctx, EVP(ctx, 0, 2)));
+    for (int j = 0; j < 3; j++) CK(rec_event(ctx, EVP(ctx, 1, j)));        // second projector: inside the same launches
+    ctx->phase_events = true;
+    k_finalize_sum_sampled<<<dim3(FIN_BLOCKS, 2), 1024, 0, ctx->stream>>>(ctx->d_recs, ctx->d_zw, n, ctx->t, ctx->d_per, RED(ctx),
+                                                                          ctx->d_partials, ctx->d_ticket, 4);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
     return 0;
@@ -1108,6 +1157,11 @@ static int run_bin(bg_ctx* ctx, int bin, int red_slot) {
 // enqueue the whole prepared job (all projectors, all bins) on ctx's stream
 static int enqueue_job(bg_ctx* ctx) {
     CK(rec_event(ctx, EV0(ctx)));
+    if (fused2(ctx)) {
+        if (run_fused2(ctx)) return 1;
+        CK(rec_event(ctx, EV1(ctx)));
+        return 0;
+    }
     for (int pj = 0; pj < ctx->nproj; pj++) {
         ctx->cur = pj;
         for (int b = 0; b < ctx->bins; b++) if (run_bin(ctx, b, 4 * pj + b)) { ctx->cur = 0; return 1; }
@@ -1209,7 +1263,9 @@ static int sampled_finish_n(bg_ctx* ctx, double* out) {
     cudaError_t e = cudaEventSynchronize(ctx->ev_out[ctx->slot]);
     if (e != cudaSuccess) { ctx->slot = 0; return fail(ctx, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)); }
     ctx->stats.d2h_bytes = (uint64_t)ctx->nproj * ctx->bins * sizeof(double);
-    if (ctx->use_graph) ctx->stats.launches = (uint64_t)ctx->nproj * ctx->bins * 4;   // prepare, 2 x pairs, finalize per bin
+    if (ctx->use_graph)           // prepare, 2 x pairs, finalize: per projector and bin, or once for a fused two-projector job
+        ctx->stats.launches = fused2(ctx) ? 4 : (uint64_t)ctx->nproj * ctx->bins * 4;
+    ctx->stats.pair_launches = fused2(ctx) ? 1 : (uint64_t)ctx->nproj * ctx->bins;
     ctx->phase_events = true;
     const int rc = collect_stats(ctx, ctx->nproj, true);
     for (int pj = 0; pj < ctx->nproj && !rc; pj++) {

@@ -165,7 +165,8 @@ int  bg_decomposition_terms(bg_ctx* ctx, uint64_t first, size_t count, bg_state*
 typedef struct bg_stats {
     double   kernel_ms;        /* CUDA-event time of the last hot-path kernel(s), on ctx's stream */
     uint64_t pairs;            /* inner products evaluated by this rank in the last call          */
-    uint64_t reserved;
+    uint64_t pair_launches;    /* launches of the pair kernel proper in the last call (1 for a fused
+                                  two-projector job, else one per projector and bin)                   */
     uint64_t launches;         /* kernels launched by the last call                               */
     uint64_t h2d_bytes;        /* host->device bytes moved by the last call                       */
     uint64_t d2h_bytes;        /* device->host bytes moved by the last call                       */

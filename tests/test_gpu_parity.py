@@ -390,6 +390,10 @@ def test_two_projector_job_and_graph_replay(be):
     be.sampled_prepare2(g, h, 3000, 1, 31, 32)
     be.sampled_run()
     assert be.sampled_finish2(1.0) == (a, b)
+    # ... and is one fused launch sequence for both projectors (prepare, pairs, pairs[many checks], finalize)
+    st = be.stats()
+    assert st["pair_launches"] == 1 and st["launches"] == 4
+    assert 0 < st["pairs"] <= 2 * 3000 * exact_terms(cfg["t"])          # annihilated samples meet no term
 
 
 def test_pipelined_runs_two_in_flight(be):
