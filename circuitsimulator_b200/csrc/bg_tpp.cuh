@@ -274,6 +274,101 @@ BG_HD void t_xor4(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2
 #endif
 }
 
+// ... and three updates at once (the first pass of the rounds carries the pending fold along)
+BG_HD void t_xor6(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2, uint32_t M3, uint32_t V3,
+                  uint32_t M4, uint32_t V4, uint32_t M5, uint32_t V5, uint32_t M6, uint32_t V6) {
+    uint32_t U = M1 | M2 | M3 | M4 | M5 | M6;
+    BG_TRACE(tpopc(U), 0);
+#if defined(__CUDA_ARCH__)
+    while (U) {
+        const uint32_t c = (uint32_t)thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        const uint32_t addr = c * J.sstride + J.sbase;
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+        asm("{\n\t.reg .pred p, q, r, s, t, u;\n\t"
+            "setp.ne.u32 p, %1, 0;\n\tsetp.ne.u32 q, %2, 0;\n\tsetp.ne.u32 r, %3, 0;\n\tsetp.ne.u32 s, %4, 0;\n\t"
+            "setp.ne.u32 t, %5, 0;\n\tsetp.ne.u32 u, %6, 0;\n\t"
+            "@p xor.b32 %0, %0, %7;\n\t@q xor.b32 %0, %0, %8;\n\t@r xor.b32 %0, %0, %9;\n\t@s xor.b32 %0, %0, %10;\n\t"
+            "@t xor.b32 %0, %0, %11;\n\t@u xor.b32 %0, %0, %12;\n\t}"
+            : "+r"(r) : "r"(M1 & b), "r"(M2 & b), "r"(M3 & b), "r"(M4 & b), "r"(M5 & b), "r"(M6 & b),
+              "r"(V1), "r"(V2), "r"(V3), "r"(V4), "r"(V5), "r"(V6));
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(r) : "memory");
+    }
+#else
+    while (U) {
+        const int c = thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+        uint32_t r = J.get(c);
+        if (M1 & b) r ^= V1;
+        if (M2 & b) r ^= V2;
+        if (M3 & b) r ^= V3;
+        if (M4 & b) r ^= V4;
+        if (M5 & b) r ^= V5;
+        if (M6 & b) r ^= V6;
+        J.put(c, r);
+        BG_WORK(rows, 1);
+        BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0) + ((M3 & b) ? 1 : 0) + ((M4 & b) ? 1 : 0) + ((M5 & b) ? 1 : 0) + ((M6 & b) ? 1 : 0));
+    }
+#endif
+}
+BG_HD void t_xor6(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2, uint64_t M3, uint64_t V3,
+                  uint64_t M4, uint64_t V4, uint64_t M5, uint64_t V5, uint64_t M6, uint64_t V6) {
+    BG_TRACE(tpopc((uint32_t)(M1 | M2 | M3 | M4 | M5 | M6)), tpopc((uint32_t)((M1 | M2 | M3 | M4 | M5 | M6) >> 32)));
+#if defined(__CUDA_ARCH__)
+    const uint32_t v1l = (uint32_t)V1, v1h = (uint32_t)(V1 >> 32), v2l = (uint32_t)V2, v2h = (uint32_t)(V2 >> 32);
+    const uint32_t v3l = (uint32_t)V3, v3h = (uint32_t)(V3 >> 32), v4l = (uint32_t)V4, v4h = (uint32_t)(V4 >> 32);
+    const uint32_t v5l = (uint32_t)V5, v5h = (uint32_t)(V5 >> 32), v6l = (uint32_t)V6, v6h = (uint32_t)(V6 >> 32);
+#pragma unroll
+    for (int h = 1; h >= 0; h--) {
+        const uint32_t m1 = (uint32_t)(M1 >> (32 * h)), m2 = (uint32_t)(M2 >> (32 * h)), m3 = (uint32_t)(M3 >> (32 * h));
+        const uint32_t m4 = (uint32_t)(M4 >> (32 * h)), m5 = (uint32_t)(M5 >> (32 * h)), m6 = (uint32_t)(M6 >> (32 * h));
+        const uint32_t hbase = J.sbase + (uint32_t)(32 * h) * J.sstride;
+        uint32_t U = m1 | m2 | m3 | m4 | m5 | m6;
+        while (U) {
+            const uint32_t c = (uint32_t)thighest(U);
+            const uint32_t b = 1u << c;
+            U ^= b;
+            const uint32_t addr = c * J.sstride + hbase;
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+            asm("{\n\t.reg .pred p, q, r, s, t, u;\n\t"
+                "setp.ne.u32 p, %2, 0;\n\tsetp.ne.u32 q, %3, 0;\n\tsetp.ne.u32 r, %4, 0;\n\tsetp.ne.u32 s, %5, 0;\n\t"
+                "setp.ne.u32 t, %6, 0;\n\tsetp.ne.u32 u, %7, 0;\n\t"
+                "@p xor.b32 %0, %0, %8;\n\t@p xor.b32 %1, %1, %9;\n\t"
+                "@q xor.b32 %0, %0, %10;\n\t@q xor.b32 %1, %1, %11;\n\t"
+                "@r xor.b32 %0, %0, %12;\n\t@r xor.b32 %1, %1, %13;\n\t"
+                "@s xor.b32 %0, %0, %14;\n\t@s xor.b32 %1, %1, %15;\n\t"
+                "@t xor.b32 %0, %0, %16;\n\t@t xor.b32 %1, %1, %17;\n\t"
+                "@u xor.b32 %0, %0, %18;\n\t@u xor.b32 %1, %1, %19;\n\t}"
+                : "+r"(lo), "+r"(hi) : "r"(m1 & b), "r"(m2 & b), "r"(m3 & b), "r"(m4 & b), "r"(m5 & b), "r"(m6 & b),
+                  "r"(v1l), "r"(v1h), "r"(v2l), "r"(v2h), "r"(v3l), "r"(v3h), "r"(v4l), "r"(v4h),
+                  "r"(v5l), "r"(v5h), "r"(v6l), "r"(v6h));
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(lo), "r"(hi) : "memory");
+        }
+    }
+#else
+    uint64_t U = M1 | M2 | M3 | M4 | M5 | M6;
+    while (U) {
+        const int c = thighest(U);
+        const uint64_t b = 1ull << c;
+        U ^= b;
+        uint64_t r = J.get(c);
+        if (M1 & b) r ^= V1;
+        if (M2 & b) r ^= V2;
+        if (M3 & b) r ^= V3;
+        if (M4 & b) r ^= V4;
+        if (M5 & b) r ^= V5;
+        if (M6 & b) r ^= V6;
+        J.put(c, r);
+        BG_WORK(rows, 1);
+        BG_WORK(xors, ((M1 & b) ? 1 : 0) + ((M2 & b) ? 1 : 0) + ((M3 & b) ? 1 : 0) + ((M4 & b) ? 1 : 0) + ((M5 & b) ? 1 : 0) + ((M6 & b) ? 1 : 0));
+    }
+#endif
+}
+
 // x_i = x'_i + sum_{a in Sp} x'_a.   (bg_device.cuh: basis_change)   Returns the old row i.
 template <typename W> BG_HD W t_basis_change(const Rows<W>& J, TF<W>& f, int i, W Sp) {
     const W bi = tbit<W>(i);
@@ -302,69 +397,23 @@ template <typename W> BG_HD void t_pivot(const Rows<W>& J, TF<W>& f, W S, uint32
     f.A &= ~bi;
 }
 
-// One elimination step's bookkeeping: variable a (bit ba) with partner b (bit bb; = ba for a monomer),
-// M1 / M2 = the remaining rows c with J_ca / J_cb.  `on` = false turns the step into a no-op.
-template <typename W>
-BG_HD void t_step_scalars(W& D2, W& Js, W ba, W bb, bool on, bool dimer, W M1, W M2,
-                          uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1) {
-    const bool d2a = (D2 & ba) != 0, sa = (Js & ba) != 0;
-    const bool d2b = (D2 & bb) != 0, sb = (Js & bb) != 0;
-    cnt += on ? 1u : 0u;
-    neg0 ^= (uint32_t)(dimer & d2a & d2b);
-    neg1 ^= (uint32_t)(dimer & (d2a ^ sa) & (d2b ^ sb));
-    z0 |= (uint32_t)(on & !dimer & d2a);
-    z1 |= (uint32_t)(on & !dimer & (d2a ^ sa));
-    D2 ^= (d2b ? M1 : (W)0) ^ (d2a ? M2 : (W)0) ^ (M1 & M2);
-    Js ^= (sb ? M1 : (W)0) ^ (sa ? M2 : (W)0);
-}
+// =====================================================================================================
+// The monomer / dimer steps of the exponential sum on the variables in E (all with D in {0,4}).
+//
+// * TWO steps per pass over the rows (t_xor4): step 2 picks its variables from the rows a2, b2 brought up
+//   to date with step 1 on the fly; every other remaining row gets both updates in one touch.  A row is
+//   touched when any of its four bits is set (15/16 of the rows instead of 3/4, twice), so the trip
+//   counts of the 32 lanes of a warp are nearly equal.
+// * No branch in the body: a monomer {a} is a dimer whose update masks are empty, and a missing second
+//   step is a step with all masks empty — the lanes of a warp stay together.
+// * The fold that precedes the rounds (t_expsum) is not applied to the rows either: it is handed over as a
+//   PENDING update (TPend) and rides along with the first pass (t_xor6), fixed up on the fly in the rows
+//   that pass reads.
+// * Bits of D2 / Js are taken with one (funnel) shift and kept as "bit 0 of a word" (upper bits are junk
+//   until the end); conditional xors are predicated.
+// =====================================================================================================
+template <typename W> struct TPend { W M1, V1, M2, V2; };     // row_c ^= [c in M1] V1 ^ [c in M2] V2, not yet applied
 
-// The monomer / dimer steps of the exponential sum on the variables in E (all with D in {0,4}), TWO steps
-// per pass over the rows.  No branch in the body: a monomer {a} is a dimer whose update masks are empty,
-// and a missing second step is a step with all masks empty — the 32 lanes of a warp stay together, only
-// the row loop of t_xor4 has per-lane trip counts.  Step 2 picks its variables from the rows a2, b2
-// brought up to date with step 1 on the fly; every other remaining row gets both updates in one touch.
-template <typename W>
-BG_HD void t_rounds(const Rows<W>& J, W& E, W& D2, W& Js, uint32_t& cnt, uint32_t& neg0, uint32_t& neg1,
-                    uint32_t& z0, uint32_t& z1, bool has_s) {
-    while (E != 0) {
-        // ---- step 1: a = highest variable left, b = its highest neighbour
-        const int a = thighest(E);
-        const W ba = tbit<W>(a);
-        const W Ja = J.get(a) & E & ~ba;
-        const bool dim1 = Ja != 0;
-        const int b = dim1 ? thighest(Ja) : a;
-        const W bb = tbit<W>(b);
-        const W rest1 = E & ~(ba | bb);
-        const W M1 = Ja & rest1;
-        const W M2 = dim1 ? (J.get(b) & rest1) : (W)0;
-        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
-        t_step_scalars<W>(D2, Js, ba, bb, true, dim1, M1, M2, cnt, neg0, neg1, z0, z1);
-        const bool stop1 = z0 && (z1 || !has_s);                        // the whole sum is zero
-        // ---- step 2 on what is left
-        const W left = stop1 ? (W)0 : rest1;
-        const bool on2 = left != 0;
-        const int a2 = on2 ? thighest(left) : a;
-        const W ba2 = on2 ? tbit<W>(a2) : (W)0;
-        const W ra = J.get(a2) ^ ((M1 & ba2) ? M2 : (W)0) ^ ((M2 & ba2) ? M1 : (W)0);
-        const W Ja2 = ra & left & ~ba2;
-        const bool dim2 = Ja2 != 0;
-        const int b2 = dim2 ? thighest(Ja2) : a2;
-        const W bb2 = on2 ? tbit<W>(b2) : (W)0;
-        const W rb = J.get(b2) ^ ((M1 & bb2) ? M2 : (W)0) ^ ((M2 & bb2) ? M1 : (W)0);
-        const W rest2 = left & ~(ba2 | bb2);
-        const W M3 = Ja2 & rest2;
-        const W M4 = dim2 ? (rb & rest2) : (W)0;
-        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (on2 && !dim2) ? 1 : 0);
-        t_step_scalars<W>(D2, Js, ba2, bb2, on2, dim2, M3, M4, cnt, neg0, neg1, z0, z1);
-        // ---- both updates on the rows that stay:  J_c ^= [J_ca] J_b ^ [J_cb] J_a, twice
-        t_xor4(J, M1 & rest2, M2, M2 & rest2, M1, M3, M4, M4, M3);
-        E = (z0 && (z1 || !has_s)) ? (W)0 : rest2;
-    }
-}
-
-// ---- the same two-step rounds for 32-bit words (t <= 32, and the tail of the 64-bit case) -----------
-// Bits of D2 / Js are taken with one shift and kept as "bit 0 of a word" (upper bits are junk until the
-// end); conditional xors are predicated.
 BG_HD void t_cxor32(uint32_t& x, uint32_t c, uint32_t v) {            // x ^= v if c & 1
 #if defined(__CUDA_ARCH__)
     asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, 1;\n\tsetp.ne.u32 p, t, 0;\n\t@p xor.b32 %0, %0, %2;\n\t}"
@@ -385,49 +434,60 @@ BG_HD void t_step_scalars32(uint32_t& D2, uint32_t& Js, uint32_t ia, uint32_t ib
     t_cxor32(D2, d2b, M1); t_cxor32(D2, d2a, M2); D2 ^= M1 & M2;
     t_cxor32(Js, sb, M1); t_cxor32(Js, sa, M2);
 }
+// row `i` as the pending update leaves it
+template <bool PEND> BG_HD uint32_t t_row32(const Rows<uint32_t>& J, uint32_t i, const TPend<uint32_t>& pd) {
+    uint32_t r = J.get((int)i);
+    if (PEND) { t_cxor32(r, pd.M1 >> i, pd.V1); t_cxor32(r, pd.M2 >> i, pd.V2); }
+    return r;
+}
+// two steps + one pass (32-bit words)
+template <bool PEND>
+BG_HD void t_block32(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_t& Js, uint32_t& cnt, uint32_t& neg0,
+                     uint32_t& neg1, uint32_t& z0, uint32_t& z1, uint32_t ns, const TPend<uint32_t>& pd) {
+    // ---- step 1: a = highest variable left, b = its highest neighbour (a itself: monomer)
+    const uint32_t a = (uint32_t)thighest(E), ba = 1u << a;
+    const uint32_t Ja = t_row32<PEND>(J, a, pd) & E & ~ba;
+    const bool dim1 = Ja != 0u;
+    const uint32_t dm1 = dim1 ? ~0u : 0u;
+    const uint32_t b = (uint32_t)thighest(dim1 ? Ja : ba), bb = 1u << b;
+    const uint32_t r1 = E & ~(ba | bb);
+    const uint32_t M1 = Ja & r1;
+    const uint32_t M2 = t_row32<PEND>(J, b, pd) & r1 & dm1;
+    BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
+    t_step_scalars32(D2, Js, a, b, 1u, ~0u, dm1, M1, M2, cnt, neg0, neg1, z0, z1);
+    // ---- step 2 on what is left (nothing, if the sum is already known to vanish)
+    const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & (r1 != 0u);
+    const uint32_t left = go2 ? r1 : 0u;
+    const uint32_t a2 = (uint32_t)thighest(go2 ? r1 : ba), ba2 = 1u << a2;
+    uint32_t q = t_row32<PEND>(J, a2, pd);
+    t_cxor32(q, M1 >> a2, M2); t_cxor32(q, M2 >> a2, M1);               // row a2 brought up to date with step 1
+    const uint32_t Ka = q & left & ~ba2;
+    const bool dim2 = Ka != 0u;
+    const uint32_t dm2 = dim2 ? ~0u : 0u;
+    const uint32_t b2 = (uint32_t)thighest(dim2 ? Ka : ba2), bb2 = 1u << b2;
+    uint32_t r = t_row32<PEND>(J, b2, pd);
+    t_cxor32(r, M1 >> b2, M2); t_cxor32(r, M2 >> b2, M1);
+    const uint32_t r2 = left & ~(ba2 | bb2);
+    const uint32_t M3 = Ka & r2;
+    const uint32_t M4 = r & r2 & dm2;
+    BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
+    t_step_scalars32(D2, Js, a2, b2, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3, M4, cnt, neg0, neg1, z0, z1);
+    // ---- the updates on the rows that stay:  J_c ^= [J_ca] J_b ^ [J_cb] J_a, twice (+ the pending one)
+    if (PEND) t_xor6(J, M1 & r2, M2, M2 & r2, M1, M3, M4, M4, M3, pd.M1 & r2, pd.V1, pd.M2 & r2, pd.V2);
+    else t_xor4(J, M1 & r2, M2, M2 & r2, M1, M3, M4, M4, M3);
+    E = (z0 & (z1 | ns) & 1u) ? 0u : r2;
+}
 BG_HD void t_rounds(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_t& Js, uint32_t& cnt, uint32_t& neg0,
-                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s) {
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint32_t>& pd) {
     const uint32_t ns = has_s ? 0u : 1u;
-    while (E != 0u) {
-        // ---- step 1
-        const uint32_t a = (uint32_t)thighest(E), ba = 1u << a;
-        const uint32_t Ja = J.get((int)a) & E & ~ba;
-        const bool dim1 = Ja != 0u;
-        const uint32_t dm1 = dim1 ? ~0u : 0u;
-        const uint32_t b = (uint32_t)thighest(dim1 ? Ja : ba), bb = 1u << b;
-        const uint32_t r1 = E & ~(ba | bb);
-        const uint32_t M1 = Ja & r1;
-        const uint32_t M2 = J.get((int)b) & r1 & dm1;
-        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
-        t_step_scalars32(D2, Js, a, b, 1u, ~0u, dm1, M1, M2, cnt, neg0, neg1, z0, z1);
-        // ---- step 2
-        const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & (r1 != 0u);
-        const uint32_t left = go2 ? r1 : 0u;
-        const uint32_t a2 = (uint32_t)thighest(go2 ? r1 : ba), ba2 = 1u << a2;
-        uint32_t q = J.get((int)a2);
-        t_cxor32(q, M1 >> a2, M2); t_cxor32(q, M2 >> a2, M1);
-        const uint32_t Ka = q & left & ~ba2;
-        const bool dim2 = Ka != 0u;
-        const uint32_t dm2 = dim2 ? ~0u : 0u;
-        const uint32_t b2 = (uint32_t)thighest(dim2 ? Ka : ba2), bb2 = 1u << b2;
-        uint32_t r = J.get((int)b2);
-        t_cxor32(r, M1 >> b2, M2); t_cxor32(r, M2 >> b2, M1);
-        const uint32_t r2 = left & ~(ba2 | bb2);
-        const uint32_t M3 = Ka & r2;
-        const uint32_t M4 = r & r2 & dm2;
-        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
-        t_step_scalars32(D2, Js, a2, b2, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3, M4, cnt, neg0, neg1, z0, z1);
-        t_xor4(J, M1 & r2, M2, M2 & r2, M1, M3, M4, M4, M3);
-        E = (z0 & (z1 | ns) & 1u) ? 0u : r2;
-    }
+    if (E != 0u) t_block32<true>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, ns, pd);
+    while (E != 0u) t_block32<false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, ns, pd);
     neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
 }
 
-// ---- the same two-step rounds for 64-bit words, written on 32-bit halves ----------------------------
-// (t > 32.)  The generic version above is correct for uint64_t too, but every 64-bit test / select / shift
-// costs the compiler two or three instructions; here a variable is (bit as two halves, index, row
-// address), bits of D2 / Js are taken with ONE funnel shift and kept as "bit 0 of a word" (upper bits are
-// junk until the end), conditional xors are predicated.
+// ---- the same for 64-bit words (t > 32), written on 32-bit halves: every 64-bit test / select / shift
+// would cost the compiler two or three instructions; here a variable is (bit as two halves, index, row
+// address).
 struct TIdx {
     uint32_t bl, bh;       // the variable's bit, low and high half
     uint32_t idx;          // 0..63
@@ -443,13 +503,6 @@ BG_HD TIdx t_top64(uint32_t xl, uint32_t xh, const Rows<uint64_t>& J) {      // 
     r.addr = c * J.sstride + (ph ? J.sbase + 32u * J.sstride : J.sbase);
     return r;
 }
-BG_HD void t_ld64(const Rows<uint64_t>& J, const TIdx& i, uint32_t& l, uint32_t& h) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(h) : "r"(i.addr));
-#else
-    const uint64_t v = J.get((int)i.idx); l = (uint32_t)v; h = (uint32_t)(v >> 32);
-#endif
-}
 BG_HD uint32_t t_bit64(uint32_t l, uint32_t h, uint32_t idx) {             // bit idx of (h:l) -> bit 0 (rest: junk)
     return (uint32_t)((((uint64_t)h << 32) | l) >> idx);
 }
@@ -461,7 +514,19 @@ BG_HD void t_cxor64(uint32_t& l, uint32_t& h, uint32_t c, uint32_t vl, uint32_t 
     if (c & 1u) { l ^= vl; h ^= vh; }
 #endif
 }
-// bookkeeping of one step (cf. t_step_scalars): on = 0/1, onm / dm = all-ones masks for "step exists" / "dimer"
+struct TPend64 { uint32_t M1l, M1h, V1l, V1h, M2l, M2h, V2l, V2h; };
+template <bool PEND> BG_HD void t_ld64(const Rows<uint64_t>& J, const TIdx& i, const TPend64& pd, uint32_t& l, uint32_t& h) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(l), "=r"(h) : "r"(i.addr));
+#else
+    const uint64_t v = J.get((int)i.idx); l = (uint32_t)v; h = (uint32_t)(v >> 32);
+#endif
+    if (PEND) {
+        t_cxor64(l, h, t_bit64(pd.M1l, pd.M1h, i.idx), pd.V1l, pd.V1h);
+        t_cxor64(l, h, t_bit64(pd.M2l, pd.M2h, i.idx), pd.V2l, pd.V2h);
+    }
+}
+// bookkeeping of one step: on = 0/1, onm / dm = all-ones masks for "step exists" / "dimer"
 BG_HD void t_step_scalars64(uint32_t& D2l, uint32_t& D2h, uint32_t& Jsl, uint32_t& Jsh, uint32_t ia, uint32_t ib,
                             uint32_t on, uint32_t onm, uint32_t dm, uint32_t M1l, uint32_t M1h, uint32_t M2l, uint32_t M2h,
                             uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1) {
@@ -481,68 +546,92 @@ BG_HD void t_step_scalars64(uint32_t& D2l, uint32_t& D2h, uint32_t& Jsl, uint32_
 }
 BG_HD uint64_t t_mk64(uint32_t l, uint32_t h) { return ((uint64_t)h << 32) | l; }
 
+template <bool PEND>
+BG_HD void t_block64(const Rows<uint64_t>& J, uint32_t& El, uint32_t& Eh, uint32_t& D2l, uint32_t& D2h, uint32_t& Jsl,
+                     uint32_t& Jsh, uint32_t& cnt, uint32_t& neg0, uint32_t& neg1, uint32_t& z0, uint32_t& z1, uint32_t ns,
+                     const TPend64& pd) {
+    // ---- step 1
+    const TIdx a = t_top64(El, Eh, J);
+    uint32_t ral, rah;
+    t_ld64<PEND>(J, a, pd, ral, rah);
+    const uint32_t Jal = ral & El & ~a.bl, Jah = rah & Eh & ~a.bh;
+    const bool dim1 = (Jal | Jah) != 0u;
+    const uint32_t dm1 = dim1 ? ~0u : 0u;
+    const TIdx b = t_top64(dim1 ? Jal : a.bl, dim1 ? Jah : a.bh, J);
+    uint32_t rbl, rbh;
+    t_ld64<PEND>(J, b, pd, rbl, rbh);
+    const uint32_t r1l = El & ~(a.bl | b.bl), r1h = Eh & ~(a.bh | b.bh);
+    const uint32_t M1l = Jal & r1l, M1h = Jah & r1h;
+    const uint32_t M2l = rbl & r1l & dm1, M2h = rbh & r1h & dm1;
+    BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
+    t_step_scalars64(D2l, D2h, Jsl, Jsh, a.idx, b.idx, 1u, ~0u, dm1, M1l, M1h, M2l, M2h, cnt, neg0, neg1, z0, z1);
+    // ---- step 2
+    const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & ((r1l | r1h) != 0u);
+    const uint32_t ll = go2 ? r1l : 0u, lh = go2 ? r1h : 0u;
+    const TIdx a2 = t_top64(go2 ? r1l : a.bl, go2 ? r1h : a.bh, J);
+    uint32_t ql, qh;
+    t_ld64<PEND>(J, a2, pd, ql, qh);
+    t_cxor64(ql, qh, t_bit64(M1l, M1h, a2.idx), M2l, M2h);              // row a2 brought up to date with step 1
+    t_cxor64(ql, qh, t_bit64(M2l, M2h, a2.idx), M1l, M1h);
+    const uint32_t Kal = ql & ll & ~a2.bl, Kah = qh & lh & ~a2.bh;
+    const bool dim2 = (Kal | Kah) != 0u;
+    const uint32_t dm2 = dim2 ? ~0u : 0u;
+    const TIdx b2 = t_top64(dim2 ? Kal : a2.bl, dim2 ? Kah : a2.bh, J);
+    uint32_t sl, sh;
+    t_ld64<PEND>(J, b2, pd, sl, sh);
+    t_cxor64(sl, sh, t_bit64(M1l, M1h, b2.idx), M2l, M2h);
+    t_cxor64(sl, sh, t_bit64(M2l, M2h, b2.idx), M1l, M1h);
+    const uint32_t r2l = ll & ~(a2.bl | b2.bl), r2h = lh & ~(a2.bh | b2.bh);
+    const uint32_t M3l = Kal & r2l, M3h = Kah & r2h;
+    const uint32_t M4l = sl & r2l & dm2, M4h = sh & r2h & dm2;
+    BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
+    t_step_scalars64(D2l, D2h, Jsl, Jsh, a2.idx, b2.idx, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3l, M3h, M4l, M4h,
+                     cnt, neg0, neg1, z0, z1);
+    // ---- the updates on the rows that stay
+    if (PEND)
+        t_xor6(J, t_mk64(M1l & r2l, M1h & r2h), t_mk64(M2l, M2h), t_mk64(M2l & r2l, M2h & r2h), t_mk64(M1l, M1h),
+               t_mk64(M3l, M3h), t_mk64(M4l, M4h), t_mk64(M4l, M4h), t_mk64(M3l, M3h),
+               t_mk64(pd.M1l & r2l, pd.M1h & r2h), t_mk64(pd.V1l, pd.V1h), t_mk64(pd.M2l & r2l, pd.M2h & r2h), t_mk64(pd.V2l, pd.V2h));
+    else
+        t_xor4(J, t_mk64(M1l & r2l, M1h & r2h), t_mk64(M2l, M2h), t_mk64(M2l & r2l, M2h & r2h), t_mk64(M1l, M1h),
+               t_mk64(M3l, M3h), t_mk64(M4l, M4h), t_mk64(M4l, M4h), t_mk64(M3l, M3h));
+    const bool stop = (z0 & (z1 | ns) & 1u) != 0u;
+    El = stop ? 0u : r2l; Eh = stop ? 0u : r2h;
+}
+
 BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t& Js, uint32_t& cnt, uint32_t& neg0,
-                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s) {
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint64_t>& pd64) {
     uint32_t El = (uint32_t)E, Eh = (uint32_t)(E >> 32);
     uint32_t D2l = (uint32_t)D2, D2h = (uint32_t)(D2 >> 32), Jsl = (uint32_t)Js, Jsh = (uint32_t)(Js >> 32);
     const uint32_t ns = has_s ? 0u : 1u;
-    while ((El | Eh) != 0u) {
-        // Variables are eliminated from the top, so the high halves die first: once no lane of the warp has
-        // a variable >= 32 left, the rounds continue on the low halves of the same rows with 32-bit code.
+    TPend64 pd;
+    pd.M1l = (uint32_t)pd64.M1; pd.M1h = (uint32_t)(pd64.M1 >> 32); pd.V1l = (uint32_t)pd64.V1; pd.V1h = (uint32_t)(pd64.V1 >> 32);
+    pd.M2l = (uint32_t)pd64.M2; pd.M2h = (uint32_t)(pd64.M2 >> 32); pd.V2l = (uint32_t)pd64.V2; pd.V2h = (uint32_t)(pd64.V2 >> 32);
+    // Variables are eliminated from the top, so the high halves die first: once no lane of the warp has a
+    // variable >= 32 left, the rounds continue on the low halves of the same rows with 32-bit code.
+    bool pending = true;
 #if defined(__CUDA_ARCH__)
-        if (__all_sync(__activemask(), Eh == 0u)) break;
+#define T_ALL_LOW() __all_sync(__activemask(), Eh == 0u)
 #else
-        if (Eh == 0u) break;
+#define T_ALL_LOW() (Eh == 0u)
 #endif
-        // ---- step 1: a = highest variable left, b = its highest neighbour (a itself: monomer)
-        const TIdx a = t_top64(El, Eh, J);
-        uint32_t ral, rah;
-        t_ld64(J, a, ral, rah);
-        const uint32_t Jal = ral & El & ~a.bl, Jah = rah & Eh & ~a.bh;
-        const bool dim1 = (Jal | Jah) != 0u;
-        const uint32_t dm1 = dim1 ? ~0u : 0u;
-        const TIdx b = t_top64(dim1 ? Jal : a.bl, dim1 ? Jah : a.bh, J);
-        uint32_t rbl, rbh;
-        t_ld64(J, b, rbl, rbh);
-        const uint32_t r1l = El & ~(a.bl | b.bl), r1h = Eh & ~(a.bh | b.bh);
-        const uint32_t M1l = Jal & r1l, M1h = Jah & r1h;
-        const uint32_t M2l = rbl & r1l & dm1, M2h = rbh & r1h & dm1;
-        BG_WORK(dimers, dim1 ? 1 : 0); BG_WORK(monomers, dim1 ? 0 : 1);
-        t_step_scalars64(D2l, D2h, Jsl, Jsh, a.idx, b.idx, 1u, ~0u, dm1, M1l, M1h, M2l, M2h, cnt, neg0, neg1, z0, z1);
-        // ---- step 2 on what is left (nothing, if the sum is already known to vanish)
-        const bool go2 = ((z0 & (z1 | ns) & 1u) == 0u) & ((r1l | r1h) != 0u);
-        const uint32_t ll = go2 ? r1l : 0u, lh = go2 ? r1h : 0u;
-        const TIdx a2 = t_top64(go2 ? r1l : a.bl, go2 ? r1h : a.bh, J);
-        uint32_t ql, qh;
-        t_ld64(J, a2, ql, qh);
-        t_cxor64(ql, qh, t_bit64(M1l, M1h, a2.idx), M2l, M2h);              // row a2 brought up to date with step 1
-        t_cxor64(ql, qh, t_bit64(M2l, M2h, a2.idx), M1l, M1h);
-        const uint32_t Kal = ql & ll & ~a2.bl, Kah = qh & lh & ~a2.bh;
-        const bool dim2 = (Kal | Kah) != 0u;
-        const uint32_t dm2 = dim2 ? ~0u : 0u;
-        const TIdx b2 = t_top64(dim2 ? Kal : a2.bl, dim2 ? Kah : a2.bh, J);
-        uint32_t sl, sh;
-        t_ld64(J, b2, sl, sh);
-        t_cxor64(sl, sh, t_bit64(M1l, M1h, b2.idx), M2l, M2h);
-        t_cxor64(sl, sh, t_bit64(M2l, M2h, b2.idx), M1l, M1h);
-        const uint32_t r2l = ll & ~(a2.bl | b2.bl), r2h = lh & ~(a2.bh | b2.bh);
-        const uint32_t M3l = Kal & r2l, M3h = Kah & r2h;
-        const uint32_t M4l = sl & r2l & dm2, M4h = sh & r2h & dm2;
-        BG_WORK(dimers, dim2 ? 1 : 0); BG_WORK(monomers, (go2 && !dim2) ? 1 : 0);
-        t_step_scalars64(D2l, D2h, Jsl, Jsh, a2.idx, b2.idx, go2 ? 1u : 0u, go2 ? ~0u : 0u, dm2, M3l, M3h, M4l, M4h,
-                         cnt, neg0, neg1, z0, z1);
-        // ---- both updates on the rows that stay
-        t_xor4(J, t_mk64(M1l & r2l, M1h & r2h), t_mk64(M2l, M2h), t_mk64(M2l & r2l, M2h & r2h), t_mk64(M1l, M1h),
-               t_mk64(M3l, M3h), t_mk64(M4l, M4h), t_mk64(M4l, M4h), t_mk64(M3l, M3h));
-        const bool stop = (z0 & (z1 | ns) & 1u) != 0u;
-        El = stop ? 0u : r2l; Eh = stop ? 0u : r2h;
+    if ((El | Eh) != 0u && !T_ALL_LOW()) {
+        t_block64<true>(J, El, Eh, D2l, D2h, Jsl, Jsh, cnt, neg0, neg1, z0, z1, ns, pd);
+        pending = false;
     }
+    while ((El | Eh) != 0u) {
+        if (T_ALL_LOW()) break;
+        t_block64<false>(J, El, Eh, D2l, D2h, Jsl, Jsh, cnt, neg0, neg1, z0, z1, ns, pd);
+    }
+#undef T_ALL_LOW
     neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
     if (El != 0u) {
         Rows<uint32_t> Jl;                       // the low words of the same rows
         Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
         Jl.sbase = J.sbase; Jl.sstride = J.sstride;
-        t_rounds(Jl, El, D2l, Jsl, cnt, neg0, neg1, z0, z1, has_s);
+        TPend<uint32_t> pl;
+        pl.M1 = pending ? pd.M1l : 0u; pl.V1 = pd.V1l; pl.M2 = pending ? pd.M2l : 0u; pl.V2 = pd.V2l;
+        t_rounds(Jl, El, D2l, Jsl, cnt, neg0, neg1, z0, z1, has_s, pl);
     }
     E = 0; D2 = t_mk64(D2l, D2h); Js = t_mk64(Jsl, Jsh);
 }
@@ -554,20 +643,26 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     const bool has_s = S != 0;
     W E = A, Js = 0;
     uint32_t Ds = 0;
+    TPend<W> pd;
+    pd.M1 = pd.V1 = pd.M2 = pd.V2 = 0;
     if (has_s) {
         const int s = thighest(S);
         const W bs = tbit<W>(s), Sp = S ^ bs;
         Ds = 2u + 4u * tget(f.D2, s);
-        if (Sp) t_basis_change<W>(J, f, s, Sp);
+        // the fold x_s = x'_s + sum_{a in Sp} x'_a (t_basis_change) — its row update stays pending
+        const W Ji = J.get(s);
+        const W col = (Ji ^ ((Ji & bs) ? Sp : (W)0)) & f.A;
+        pd.M1 = Sp; pd.V1 = Ji; pd.M2 = Sp ? col : (W)0; pd.V2 = Sp;
+        BG_WORK(basis_changes, Sp ? 1 : 0);
+        const W d1s = tfill<W>(tget(f.D1, s)), d2s = tfill<W>(tget(f.D2, s));
+        f.D2 ^= Sp & (d2s ^ (d1s & f.D1) ^ Ji);
+        f.D1 ^= Sp & d1s;
         E = A & ~bs;
-        Js = J.get(s) & E;
+        Js = (Ji ^ ((col & bs) ? Sp : (W)0)) & E;        // row s after the fold (s is not in Sp)
     }
     W D2 = f.D2;
     uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
-    // (Measured and rejected: finishing the variables >= 32 first and then continuing with 32-bit words
-    // on the low halves — fewer instructions per lane, but the extra reconvergence point costs more
-    // than it saves: 4.83 vs 4.67 ms at t = 40.)
-    t_rounds(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s);
+    t_rounds(J, E, D2, Js, cnt, neg0, neg1, z0, z1, has_s, pd);
     p = 2 * (int)cnt;
     const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
     if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; return; }
