@@ -439,6 +439,10 @@ def main():
         launches_per_step = max(1, pair_launches) / args.steps
         per_launch_pairs = 2 * samples * chi / world / launches_per_step
         k_ms = pairs_ms / max(1, pair_launches)
+        # DRAM bytes of one launch from the ncu --set full capture (profiles/), scaled to this launch's pairs
+        traffic = wm.get("dram_bytes_per_launch")
+        if traffic and wm.get("pairs_per_launch_ncu"):
+            traffic = traffic * per_launch_pairs / wm["pairs_per_launch_ncu"]
         roof = {"bound": "int_alu", "unit": "Tlaneop/s",
                 "kernel": "k_pairs_tpp", "kernel_ms": k_ms, "launches_per_step": launches_per_step,
                 "pairs_per_launch": per_launch_pairs,
@@ -450,8 +454,8 @@ def main():
                 "popc_peak": popc_peak / 1e12,
                 "lane_ops_per_pair": lane_ops,
                 "pipe_busy_ncu": wm.get("alu_pipe_busy_pct"), "active_lanes_ncu": wm.get("active_lanes_per_inst"),
-                "traffic": wm.get("dram_bytes_per_launch"),
-                "hbm_gbs_achieved": (wm.get("dram_bytes_per_launch") / (k_ms * 1e-3) / 1e9) if wm.get("dram_bytes_per_launch") and k_ms > 0 else None,
+                "traffic": traffic,
+                "hbm_gbs_achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic and k_ms > 0 else None,
                 "hbm_gbs_peak": peaks.get("hbm_gbs")}
         roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["achieved"] else None
         line = {"metric": "stabilizer inner products/sec", "value": value, "unit": "inner products/s",
