@@ -478,9 +478,9 @@ BG_HD void t_block32(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_
     E = (z0 & (z1 | ns) & 1u) ? 0u : r2;
 }
 BG_HD void t_rounds(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_t& Js, uint32_t& cnt, uint32_t& neg0,
-                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint32_t>& pd) {
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint32_t>& pd, bool pending = true) {
     const uint32_t ns = has_s ? 0u : 1u;
-    if (E != 0u) t_block32<true>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, ns, pd);
+    if (pending && E != 0u) t_block32<true>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, ns, pd);
     while (E != 0u) t_block32<false>(J, E, D2, Js, cnt, neg0, neg1, z0, z1, ns, pd);
     neg0 &= 1u; neg1 &= 1u; z0 &= 1u; z1 &= 1u;
 }
@@ -630,8 +630,8 @@ BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t
         Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
         Jl.sbase = J.sbase; Jl.sstride = J.sstride;
         TPend<uint32_t> pl;
-        pl.M1 = pending ? pd.M1l : 0u; pl.V1 = pd.V1l; pl.M2 = pending ? pd.M2l : 0u; pl.V2 = pd.V2l;
-        t_rounds(Jl, El, D2l, Jsl, cnt, neg0, neg1, z0, z1, has_s, pl);
+        pl.M1 = pd.M1l; pl.V1 = pd.V1l; pl.M2 = pd.M2l; pl.V2 = pd.V2l;
+        t_rounds(Jl, El, D2l, Jsl, cnt, neg0, neg1, z0, z1, has_s, pl, pending);
     }
     E = 0; D2 = t_mk64(D2l, D2h); Js = t_mk64(Jsl, Jsh);
 }
