@@ -34,9 +34,12 @@
 
 using namespace bg;
 
-#ifndef BG_TPP_MAX_THREADS
-#define BG_TPP_MAX_THREADS 128          // largest CTA of k_pairs_tpp (BG_TPP_WARPS * 32)
+// CTA size of k_pairs_tpp, a compile-time constant: the byte stride between a thread's working rows
+// (threads x word size) then folds into immediate offsets.  3 warps: 6 CTAs per SM at t = 40.
+#ifndef BG_TPP_WARPS
+#define BG_TPP_WARPS 3
 #endif
+#define BG_TPP_THREADS (32 * BG_TPP_WARPS)
 
 // ------------------------------------------------------------------------------------------
 // device-side records
@@ -300,10 +303,11 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
 __host__ __device__ __forceinline__ int tpp_amb_rows(int t, bool manyc) { return ((manyc ? 2 * t : t) + 3) & ~3; }
 
 template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
-__global__ void __launch_bounds__(BG_TPP_MAX_THREADS) k_pairs_tpp(PairArgs a) {
+__global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
-    const int lane = bg_lane(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = bg_lane(), warp = threadIdx.x >> 5;
+    constexpr int nwarps = BG_TPP_WARPS;
     const int t = a.t;
     if (MANYC && *a.n_warp_routed == 0ull) return;      // nothing has more than TPP_MAXC parity checks
     // per warp: t ambient rows (+ t check rows when MANYC); per thread: t working rows (+ t history rows)
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(BG_TPP_MAX_THREADS) k_pairs_tpp(PairArgs a) {
     W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * amb_rows + threadIdx.x;
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
-    Rows<W> rows; rows.base = s_rows; rows.stride = blockDim.x;
-    rows.sbase = smem_u32(s_rows); rows.sstride = blockDim.x * (uint32_t)sizeof(W);
+    Rows<W> rows; rows.base = s_rows; rows.stride = BG_TPP_THREADS;
+    rows.sbase = smem_u32(s_rows); rows.sstride = BG_TPP_THREADS * (uint32_t)sizeof(W);
 
     const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
     const int sh_ = t / 2 + 1;
@@ -590,7 +594,7 @@ struct bg_ctx {
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
     int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (wins at t = 60, loses at t = 40)
-    int tpp_warps = 3;              // warps per CTA of k_pairs_tpp (BG_TPP_WARPS): 6 CTAs/SM at t = 40
+    const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
     bg_projector* d_P = nullptr;
@@ -698,7 +702,6 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e6 = getenv("BG_LAZY")) ctx->lazy = atoi(e6) != 0;
     if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
-    if (const char* e4 = getenv("BG_TPP_WARPS")) { int v = atoi(e4); if (v >= 1 && v <= BG_TPP_MAX_THREADS / 32) ctx->tpp_warps = v; }
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
     *out = ctx;
