@@ -10,7 +10,14 @@
 // Why: ncu on the warp-per-pair kernel (profiles/r1_v1_warp_per_pair_ncu_summary.json) shows the
 // integer ALU pipe 95 % busy at 1266 warp-instructions per inner product — a t = 40 term has only
 // ~20 live rows for 64 row slots and every uniform mask update is executed by all 32 lanes.  The
-// same algebra per thread needs ~2000 thread-instructions per pair, i.e. ~60 warp-instructions.
+// same algebra per thread needs ~2000 thread-instructions per pair (measured: 2080, 79 warp-instructions
+// at 26.3 active lanes, profiles/r1s3_k_pairs_tpp_ncu_summary.json).
+//
+// Structure of one inner product (t_term_L / t_term_H): working copy of the ambient rows (t_copy_in);
+// the parity checks of K_theta pivoted one by one (t_constraints -> t_pivot -> t_xor2 row pass); then the
+// exponential sum (t_expsum): the fold of the odd-D variables is computed but its row update stays
+// pending, and the monomer / dimer rounds (t_rounds -> t_block64 / t_block32) eliminate two steps per
+// pass over the rows (t_xor4; the first pass also carries the fold: t_xor6), without a branch.
 //
 // Same mathematics as bg_device.cuh (pivot / basis_change / expsum), same reference anchors:
 // shrink (stabilizer.c:500-585), updateDJ/updateQD (:129-177), exponentialSumExact (:300-481),
@@ -818,9 +825,10 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
 // SAME for all lanes of a warp.  No per-thread copy of J exists at all; the thread's shared-memory
 // rows hold the dimer history (two words per dimer, at most t/2 dimers).
 // Used for |L> terms with at most LZ_MAXB - 1 parity checks; everything else takes the eager path.
-// Measured (B200, round 1): 5.32 vs 5.78 ms at t = 60 but 5.92 vs 4.67 ms at t = 40, where the unrolled
-// basis-change entries and the history loads cost more than the divergence they remove — so it is an
-// option (BG_LAZY=1), not the default.
+// Measured (B200, round 1): against the eager kernel as first committed 5.32 vs 5.78 ms at t = 60 but
+// 5.92 vs 4.67 ms at t = 40; against the blocked eager rounds above it loses everywhere (t = 60, k = 12:
+// 149 vs 109 ms) — the blocked passes remove most of the divergence it was meant to avoid.  Kept as an
+// option (BG_LAZY=1) and as a cross-check of the eager path in the test-suite, not the default.
 #define LZ_MAXB 5                      // basis changes kept in registers: up to 4 check pivots + the fold
 template <typename W> struct LzBC { W Sp, Ji, col; };
 

@@ -593,7 +593,7 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
-    int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (wins at t = 60, loses at t = 40)
+    int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (slower than the blocked eager rounds; kept as a cross-check)
     const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
