@@ -478,6 +478,136 @@ BG_DEV void ambient(const Native<NS>& st, QForm<NS>& o, typename WordOf<NS>::T (
     Cbeta = ballotw<NS>(pb);
 }
 
+// ---------------------------------------------------------------- projection in ambient form
+// measurePauli (stabilizer.c:827-959) applied to a state that is ALREADY in ambient form:
+//   theta(x) ~ w^{q(x)} for x in K = { x : Cw_b . x = Cbeta_b, b in Cpend },  w = e^{i pi/4},
+// q = (Q, D, J) on all n bits.  With G = I every quantity of eq. 88-101 is a mask operation on the
+// computational-basis bits: no G / Gbar, no shrink / extend, no conversion afterwards.
+//
+// For P = i^m Z(zeta) X(xi):  <y|P|theta> = i^m (-1)^{zeta.y} theta(y + xi), and as polynomials
+//   q(y + xi) - q(y) = l0 + 4 (J xi).y,   l0 = D.xi + 4 sum_{q<r} J_qr xi_q xi_r   (J_qq = D1_q),
+// so with  w0 = 2m + l0 (mod 8, always even)  and  eta = zeta + J xi:
+//   xi outside the directions of K (some check has c.xi = 1): the support doubles, K' = K u (K + xi); one
+//     such check c0 is dropped (the others get += c0) and, with u(y) = c0.y + beta0 its indicator,
+//     q' = q + u(y) (w0 + 4 eta.y);                                   factor 2^-1/2   (the "extend" case)
+//   xi inside, w0 in {0,4}: theta' = theta restricted to eta.y = w0/4: a new check, or — when eta is in
+//     the span of the checks — nothing (factor 1) or annihilation;      factor 2^-1/2  (the "shrink" case)
+//   xi inside, w0 in {2,6}: theta' = 2^-1/2 theta w^{+-1 -+ 2 (eta.y mod 2)}: Q +- 1, D_q -+ 2 and
+//     J_qr ^= 1 on eta.                                                 factor 2^-1/2
+// (n (eta.y mod 2) = n sum_q - 2n e2 + ...: for n = 2, 6 that is  n sum_{q in eta} y_q + 4 sum_{q<r in eta} y_q y_r.)
+//
+// Invariant of the checks: reduced echelon form by slot — the check stored in lane slot v contains bit v and
+// no other check does (checks_echelon establishes it once).  Returns 0 (annihilated), 1 or 2 (2^-1/2).
+template <int NS>
+BG_DEV void checks_echelon(typename WordOf<NS>::T (&Cw)[NS], typename WordOf<NS>::T& Cpend, typename WordOf<NS>::T& Cbeta) {
+    typedef typename WordOf<NS>::T W;
+    const int lane = bg_lane();
+    W Cn[NS], pn = 0, bn = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) Cn[s] = 0;
+    for (W rem = Cpend; rem;) {
+        const int j = lowestw(rem);
+        rem ^= bitw<W>(j);
+        W w = rowb<NS>(Cw, j);
+        uint32_t beta = getw(Cbeta, j);
+        const W flags = w & pn;                                   // pivots of the checks already placed
+        if (flags) { w ^= xor_rows<NS>(Cn, flags); beta ^= parw(flags & bn); }
+        if (w == 0) continue;                                     // (dependent: cannot happen for rows of Gbar)
+        const int p = lowestw(w);
+        bool h[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int v = lane + 32 * s;
+            h[s] = ((pn >> v) & 1) && ((Cn[s] >> p) & 1);
+            if (h[s]) Cn[s] ^= w;
+            if (v == p) Cn[s] = w;
+        }
+        if (beta) bn ^= ballotw<NS>(h);
+        pn |= bitw<W>(p);
+        bn = (bn & ~bitw<W>(p)) | ((W)beta << p);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) Cw[s] = Cn[s];
+    Cpend = pn; Cbeta = bn;
+}
+
+template <int NS>
+BG_DEV int ambient_measure(QForm<NS>& f, typename WordOf<NS>::T (&Cw)[NS], typename WordOf<NS>::T& Cpend,
+                           typename WordOf<NS>::T& Cbeta, uint32_t m, typename WordOf<NS>::T zeta, typename WordOf<NS>::T xi) {
+    typedef typename WordOf<NS>::T W;
+    const int lane = bg_lane();
+    bool ep[NS], tp[NS], cp[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int v = lane + 32 * s;
+        const W row = f.J[s] & xi;
+        ep[s] = parw(row) != 0;                                         // (J xi)_v, diagonal J_vv = D1_v included
+        tp[s] = ((xi >> v) & 1) && parw(row & lowmaskw<W>(v));          // sum_{q<r} J_qr xi_q xi_r
+        cp[s] = ((Cpend >> v) & 1) && parw(Cw[s] & xi);                 // checks with c.xi = 1
+    }
+    const W eta = (zeta ^ ballotw<NS>(ep)) & f.A;
+    const uint32_t tri = parw(ballotw<NS>(tp));
+    const W hit = ballotw<NS>(cp);
+    const uint32_t w0 = (2u * m + 2u * (uint32_t)popcw(f.D1 & xi) + 4u * (uint32_t)popcw(f.D2 & xi) + 4u * tri) & 7u;
+    if (hit) {
+        // ---- xi leaves K: K' = K u (K + xi)
+        const int p0 = lowestw(hit);
+        const W bp0 = bitw<W>(p0);
+        const W c0 = rowb<NS>(Cw, p0);
+        const uint32_t b0 = getw(Cbeta, p0);
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int v = lane + 32 * s;
+            if (((hit >> v) & 1) && v != p0) Cw[s] ^= c0;               // the other checks become xi-invariant
+            if (v == p0) Cw[s] = 0;
+            if ((c0 >> v) & 1) f.J[s] ^= eta;                           // 4 u(y) (eta.y): J_qr ^= c0_q eta_r + c0_r eta_q
+            if ((eta >> v) & 1) f.J[s] ^= c0;
+        }
+        if (b0) Cbeta ^= hit;
+        Cbeta &= ~bp0; Cpend &= ~bp0;
+        f.D2 ^= (c0 & eta) ^ (b0 ? eta : (W)0);
+        // w0 u(y), u = beta0 + (1 - 2 beta0) (c0.y mod 2)
+        if (b0) f.Q = (f.Q + w0) & 7u;
+        const uint32_t wp = b0 ? ((8u - w0) & 7u) : w0;
+        if (wp == 4u) f.D2 ^= c0;
+        else if (wp == 2u || wp == 6u) {
+            f.D2 ^= (wp == 2u ? f.D1 : ~f.D1) & c0;                     // D_q += 2 / D_q -= 2 on c0
+            f.D1 ^= c0;
+#pragma unroll
+            for (int s = 0; s < NS; s++) if ((c0 >> (lane + 32 * s)) & 1) f.J[s] ^= c0;
+        }
+        return 2;
+    }
+    if (w0 == 0u || w0 == 4u) {
+        // ---- projector onto eta.y = w0/4 inside K
+        const W flags = eta & Cpend;
+        W er = eta;
+        uint32_t br = w0 >> 2;
+        if (flags) { er ^= xor_rows<NS>(Cw, flags); br ^= parw(flags & Cbeta); }
+        if (er == 0) return br ? 0 : 1;
+        const int p = lowestw(er);
+        bool h[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int v = lane + 32 * s;
+            h[s] = ((Cpend >> v) & 1) && ((Cw[s] >> p) & 1);
+            if (h[s]) Cw[s] ^= er;
+            if (v == p) Cw[s] = er;
+        }
+        if (br) Cbeta ^= ballotw<NS>(h);
+        Cpend |= bitw<W>(p);
+        Cbeta = (Cbeta & ~bitw<W>(p)) | ((W)br << p);
+        return 2;
+    }
+    // ---- w0 in {2,6}: 1 + w^{w(y)} = sqrt2 w^{+-1}
+    if (w0 == 2u) { f.Q = (f.Q + 1u) & 7u; f.D2 ^= eta & ~f.D1; }
+    else { f.Q = (f.Q + 7u) & 7u; f.D2 ^= eta & f.D1; }
+    f.D1 ^= eta;
+#pragma unroll
+    for (int s = 0; s < NS; s++) if ((eta >> (lane + 32 * s)) & 1) f.J[s] ^= eta;
+    return 2;
+}
+
 // ---------------------------------------------------------------- decomposition terms
 // <phi_i|theta> for phi_i = prepL(i) (stateprep.c:85-120): a product of |+> on supp(xt) and |0>
 // elsewhere.  `base` is theta's ambient form (kept intact), k1 = dim K_theta.

@@ -34,6 +34,22 @@ template <int NS> BG_DEV bool project_native(Native<NS>& st, const bg_projector*
     return true;
 }
 
+// The same on a state in ambient form (bg_device.cuh: ambient_measure) — what the hot path uses: theta is
+// converted once, right after it is drawn, and every generator is a handful of mask operations.
+template <int NS> BG_DEV bool project_ambient(Ambient<NS>& am, const bg_projector* P, int& npf) {
+    typedef typename WordOf<NS>::T W;
+    npf = 0;
+    checks_echelon<NS>(am.Cw, am.Cpend, am.Cbeta);
+    const int ns = P->nstabs;
+    for (int i = 0; i < ns; i++) {
+        const int r = ambient_measure<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, (uint32_t)P->phase[i], (W)P->zs[i], (W)P->xs[i]);
+        if (r == 0) return false;
+        if (r == 2) npf++;
+    }
+    am.k1 = popcw(am.f.A) - popcw(am.Cpend);
+    return true;
+}
+
 // innerProductExact(state1 = a, state2 = b) (stabilizer.c:589-659) for arbitrary states:
 // both become ambient forms, q = q_a - q_b on K_a ∩ K_b.
 template <int NS> BG_DEV void warp_inner_product(const bg_state* a, const bg_state* b, int& eps, int& p, int& m) {
@@ -94,8 +110,9 @@ BG_DEV void warp_sample_terms(const bg_state* theta, const bg_projector* P, int 
     {
         Native<NS> st;
         native_load<NS>(st, theta);
-        if (project) alive = project_native<NS>(st, P, npf);
-        if (alive) make_ambient<NS>(st, am); else am.k1 = 0;
+        make_ambient<NS>(st, am);
+        if (project) alive = project_ambient<NS>(am, P, npf);
+        if (!alive) am.k1 = 0;
     }
     Zw z; z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
     const int sh = t / 2 + 1;

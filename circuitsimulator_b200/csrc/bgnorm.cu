@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
         else if (SRC == SRC_STATES) native_load<NS>(st, &a.states[idx]);
         else term_native<NS>(st, a.t, a.exact, a.terms[a.first + (uint64_t)idx * a.stride]);
         if (a.raw_out) native_store_raw<NS>(st, &a.raw_out[idx], &a.raw_A[idx]);
+        // theta in ambient form first (once), then the projector's generators as mask operations on it
+        // (bg_device.cuh: ambient_measure) — no G / Gbar updates, no conversion afterwards
+        Ambient<NS> am;
+        make_ambient<NS>(st, am);
         int npf = 0;
         bool alive = true;
-        if (a.project) alive = project_native<NS>(st, P, npf);
+        if (a.project) alive = project_ambient<NS>(am, P, npf);
         SampleRec* r = &a.recs[idx];
         if (lane < 4) {
             if (a.zw) a.zw[(size_t)idx * 4 + lane] = 0;
@@ -176,8 +180,6 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
             if (lane == 0) { r->alive = 0; r->k1 = 0; r->npf = 0; r->Q = 0; }
             continue;
         }
-        Ambient<NS> am;
-        make_ambient<NS>(st, am);
         if (lane == 0) {
             const int route = a.force_warp ? ROUTE_WARP : (popcw(am.Cpend) > TPP_MAXC ? ROUTE_TPP_MANY : ROUTE_TPP);
             if (route != ROUTE_TPP) atomicAdd(a.n_warp_routed, 1ull);

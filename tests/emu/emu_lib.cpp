@@ -61,8 +61,8 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
         Native<NS> st; Ambient<NS> am;
         native_load<NS>(st, theta);
         int n = 0; bool ok = true;
-        if (project) ok = project_native<NS>(st, P, n);
-        if (ok) make_ambient<NS>(st, am);
+        make_ambient<NS>(st, am);                         // as k_prepare does: convert once, project in ambient form
+        if (project) ok = project_ambient<NS>(am, P, n);
         const int lane = bg_lane();
         if (lane == 0) { alive = ok; npf = n; }
         if (ok) {
