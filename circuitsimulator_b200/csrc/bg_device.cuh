@@ -536,18 +536,23 @@ BG_DEV int ambient_measure(QForm<NS>& f, typename WordOf<NS>::T (&Cw)[NS], typen
                            typename WordOf<NS>::T& Cbeta, uint32_t m, typename WordOf<NS>::T zeta, typename WordOf<NS>::T xi) {
     typedef typename WordOf<NS>::T W;
     const int lane = bg_lane();
-    bool ep[NS], tp[NS], cp[NS];
+    bool ep[NS], tp[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         const int v = lane + 32 * s;
         const W row = f.J[s] & xi;
         ep[s] = parw(row) != 0;                                         // (J xi)_v, diagonal J_vv = D1_v included
         tp[s] = ((xi >> v) & 1) && parw(row & lowmaskw<W>(v));          // sum_{q<r} J_qr xi_q xi_r
-        cp[s] = ((Cpend >> v) & 1) && parw(Cw[s] & xi);                 // checks with c.xi = 1
     }
     const W eta = (zeta ^ ballotw<NS>(ep)) & f.A;
     const uint32_t tri = parw(ballotw<NS>(tp));
-    const W hit = ballotw<NS>(cp);
+    W hit = 0;                                                          // checks with c.xi = 1
+    if (Cpend) {
+        bool cp[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) cp[s] = ((Cpend >> (lane + 32 * s)) & 1) && parw(Cw[s] & xi);
+        hit = ballotw<NS>(cp);
+    }
     const uint32_t w0 = (2u * m + 2u * (uint32_t)popcw(f.D1 & xi) + 4u * (uint32_t)popcw(f.D2 & xi) + 4u * tri) & 7u;
     if (hit) {
         // ---- xi leaves K: K' = K u (K + xi)
