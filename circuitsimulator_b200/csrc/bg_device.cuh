@@ -408,47 +408,62 @@ BG_DEV void ambient(const Native<NS>& st, QForm<NS>& o, typename WordOf<NS>::T (
     const int lane = bg_lane();
     const int n = st.n;
     const W A = st.f.A, maskn = lowmaskw<W>(n);
-    // R_q = column q of Gbar restricted to the rows in A
-    W R[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) R[s] = st.Gb[s];
-    transposew(R);
-#pragma unroll
-    for (int s = 0; s < NS; s++) R[s] &= A;
-    // M_q = xor_{a in R_q} J_a ;  t_q = sum_{b<a in R_q} J_ab  (strictly lower rows broadcast separately,
-    // so no per-iteration mask arithmetic; rows outside A are all-zero in R and are skipped)
-    W M[NS], Jlow[NS]; uint32_t tq[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) { M[s] = 0; tq[s] = 0; Jlow[s] = st.f.J[s] & A & lowmaskw<W>(lane + 32 * s); }
-    for (int a = 0; a < n; a++) {
-        if (!((A >> a) & 1)) continue;
-        const W Ja = rowb<NS>(st.f.J, a) & A;
-        const W Jl = rowb<NS>(Jlow, a);
-#pragma unroll
-        for (int s = 0; s < NS; s++)
-            if ((R[s] >> a) & 1) { M[s] ^= Ja; tq[s] ^= parw(Jl & R[s]); }
-    }
-    bool p1[NS], p2[NS];
+    // Are the active rows of Gbar unit vectors (Gbar_a = e_a for a in A)?  Always so for a state drawn by
+    // native_random — a lazy shrink only touches the Gbar row of the pivot it removes from A — and then the
+    // G-coordinates of x are its own bits: R is the identity on A and (D~, J~) = (D, J) on A.
+    W Dt1, Dt2, Jt[NS];
+    bool un[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) {
-        const uint32_t c1 = (uint32_t)popcw(R[s] & st.f.D1);
-        p1[s] = (c1 & 1u) != 0;
-        p2[s] = (((c1 >> 1) ^ (uint32_t)popcw(R[s] & st.f.D2) ^ tq[s]) & 1u) != 0;
+        const int v = lane + 32 * s;
+        un[s] = ((A >> v) & 1) && st.Gb[s] != bitw<W>(v);
     }
-    const W Dt1 = ballotw<NS>(p1) & maskn;
-    W Dt2 = ballotw<NS>(p2) & maskn;
-    // J~ = M R^T and R^T = Gbar[A]:  J~_q = xor_{a in M_q} Gbar_a  (M_q only has bits in A)
-    W Jt[NS];
+    if (ballotw<NS>(un) == 0) {
+        Dt1 = st.f.D1 & A; Dt2 = st.f.D2 & A;
 #pragma unroll
-    for (int s = 0; s < NS; s++) Jt[s] = 0;
-    for (int a = 0; a < n; a++) {
-        if (!((A >> a) & 1)) continue;
-        const W Ga = rowb<NS>(st.Gb, a);
+        for (int s = 0; s < NS; s++) Jt[s] = ((A >> (lane + 32 * s)) & 1) ? (st.f.J[s] & A) : (W)0;
+    } else {
+        // R_q = column q of Gbar restricted to the rows in A
+        W R[NS];
 #pragma unroll
-        for (int s = 0; s < NS; s++) if ((M[s] >> a) & 1) Jt[s] ^= Ga;
+        for (int s = 0; s < NS; s++) R[s] = st.Gb[s];
+        transposew(R);
+#pragma unroll
+        for (int s = 0; s < NS; s++) R[s] &= A;
+        // M_q = xor_{a in R_q} J_a ;  t_q = sum_{b<a in R_q} J_ab  (strictly lower rows broadcast separately,
+        // so no per-iteration mask arithmetic; rows outside A are all-zero in R and are skipped)
+        W M[NS], Jlow[NS]; uint32_t tq[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) { M[s] = 0; tq[s] = 0; Jlow[s] = st.f.J[s] & A & lowmaskw<W>(lane + 32 * s); }
+        for (int a = 0; a < n; a++) {
+            if (!((A >> a) & 1)) continue;
+            const W Ja = rowb<NS>(st.f.J, a) & A;
+            const W Jl = rowb<NS>(Jlow, a);
+#pragma unroll
+            for (int s = 0; s < NS; s++)
+                if ((R[s] >> a) & 1) { M[s] ^= Ja; tq[s] ^= parw(Jl & R[s]); }
+        }
+        bool p1[NS], p2[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const uint32_t c1 = (uint32_t)popcw(R[s] & st.f.D1);
+            p1[s] = (c1 & 1u) != 0;
+            p2[s] = (((c1 >> 1) ^ (uint32_t)popcw(R[s] & st.f.D2) ^ tq[s]) & 1u) != 0;
+        }
+        Dt1 = ballotw<NS>(p1) & maskn;
+        Dt2 = ballotw<NS>(p2) & maskn;
+        // J~ = M R^T and R^T = Gbar[A]:  J~_q = xor_{a in M_q} Gbar_a  (M_q only has bits in A)
+#pragma unroll
+        for (int s = 0; s < NS; s++) Jt[s] = 0;
+        for (int a = 0; a < n; a++) {
+            if (!((A >> a) & 1)) continue;
+            const W Ga = rowb<NS>(st.Gb, a);
+#pragma unroll
+            for (int s = 0; s < NS; s++) if ((M[s] >> a) & 1) Jt[s] ^= Ga;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) Jt[s] &= maskn;
     }
-#pragma unroll
-    for (int s = 0; s < NS; s++) Jt[s] &= maskn;
     // shift u = x + h
     const W h = st.h;
     bool pq[NS], pd[NS];
