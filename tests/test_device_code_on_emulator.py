@@ -129,3 +129,47 @@ def test_thread_per_pair_with_many_parity_checks(emu, oracle):
             for i in range(16):
                 assert epm_equal(tuple(got["epm"][i]), oracle.inner_product(s, oracle.prepL(i, t, L)))
         assert max(seen) > 6
+
+
+def test_projection_in_ambient_coordinates(emu, oracle):
+    """ambient_measure (measurePauli on a state that is already in ambient form) against the oracle's
+    measurePauli (stabilizer.c:827-959): the reference's own measurePauli KAT states and generators, and
+    random states of every dimension (many parity checks: the echelon bookkeeping, implied / contradicted
+    checks, annihilation) under random Hermitian Paulis — Z-type, X-type and mixed.  Compared through what
+    the hot path consumes: alive, the number of 2^-1/2 factors, and every <phi_i|P theta> of a |L> table."""
+    from oracle.oracle import Projector
+    rs = np.random.RandomState(17)
+    kat = load("kat_measure_pauli.npz")
+    cases = []
+    for st, m, zeta, xi in zip(states(kat["states_in"]), kat["m"], kat["zeta"], kat["xi"]):
+        cases.append((st, [(int(m), int(zeta), int(xi))]))
+    for t in (5, 12, 33, 40):
+        mask = (1 << t) - 1
+        for j in range(24):
+            s = oracle.random_state_philox(t, 21, 0, j)
+            for _ in range((j * 5) % (t + 1)):                       # lower the dimension: many parity checks
+                oracle.measure_pauli(s, 0, int(rs.randint(1, 2 ** 62)) & mask or 1, 0)
+            gens = []
+            for g in range(1 + j % 4):
+                kind = (j + g) % 3
+                x = 0 if kind == 0 else (int(rs.randint(1, 2 ** 62)) & mask or 1)
+                z = 0 if kind == 1 else (int(rs.randint(1, 2 ** 62)) & mask or 1)
+                gens.append(((bin(x & z).count("1") + 2 * int(rs.randint(0, 2))) % 4, z, x))
+            cases.append((s, gens))
+    dead = factors = 0
+    for st, gens in cases:
+        t = st.n
+        L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(3)]
+        terms = [oracle.Lbits(i, L) for i in range(8)]
+        P = Projector.make(t, [g[0] for g in gens], [g[2] for g in gens], [g[1] for g in gens])
+        want = oracle.sample_from_theta(st.copy(), P, False, L)
+        for tpp in (False, True):
+            got = emu.terms(st, P, 1, False, t, terms, tpp=tpp)
+            assert got["alive"] == want["alive"]
+            if not want["alive"]:
+                continue
+            assert abs(2 ** (-got["npf"] / 2) - want["projfactor"]) < 1e-15
+            assert all(epm_equal(tuple(got["epm"][i]), tuple(want["epm"][i])) for i in range(8))
+        dead += not want["alive"]
+        factors += want["alive"] and want["projfactor"] < 1
+    assert dead > 3 and factors > 20                                 # all the branches are exercised
