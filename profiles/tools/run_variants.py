@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Scratch harness (not product): time the pair kernel of config 4 for every library variant in profiles/tools/libs/ (listed with their BG_* environment in profiles/tools/variants.json).
-usage: python profiles/tools/run_variants.py [config] [steps]      env passes through (BG_TPP_WARPS, BG_CTAS_PER_SM, ...)"""
+usage: python profiles/tools/run_variants.py [config] [steps]      env passes through (BG_FUSE2, BG_ITEMS_FACTOR, BG_LAZY, ...)"""
 import glob, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CHILD = r'''
