@@ -1,16 +1,18 @@
 // bgnorm.cu — CUDA kernels (sm_100a) and the C ABI of include/bgnorm.h.
 //
 // Hot path = the L x chi loop of libcirc/innerprod.c:88-144 (reference repo
-// patrickrall/CircuitSimulator).  Three kernels per projector evaluation:
+// patrickrall/CircuitSimulator).  Per probability() evaluation (both projectors in one job) one launch of:
 //
-//   k_prepare  one warp per sample: draw theta on the device (Philox) or load it, apply the
-//              projector's generators (measurePauli), turn the result into its ambient
-//              quadratic form + parity checks, store a 1 KB record in HBM.
-//   k_pairs    persistent CTAs, one warp per work item (sample, chunk of terms): the chi
-//              decomposition terms are staged ONCE per CTA into shared memory with a TMA bulk
-//              copy (cp.async.bulk + mbarrier); every <phi_i|theta> is evaluated in registers
-//              (ballot / shfl / LOP3 / POPC), accumulated exactly in Z[e^{i pi/4}] as int64.
-//   k_finalize 2^t |projfactor * sum|^2 per sample in fp64 and a fixed-order tree sum.
+//   k_prepare     one warp per sample: draw theta on the device (Philox) or load it, turn it into its
+//                 ambient quadratic form + parity checks, apply the projector's generators in those
+//                 coordinates (measurePauli as mask operations), store a 1 KB record in HBM.
+//   k_pairs_tpp   persistent CTAs, one THREAD per inner product, a warp = one theta x 32 terms: the chi
+//                 decomposition terms are staged ONCE per CTA into shared memory with a TMA bulk copy
+//                 (cp.async.bulk + mbarrier); each thread eliminates its own copy of J (shared memory,
+//                 [row][thread]) two steps per row pass (bg_tpp.cuh); sums accumulated exactly in
+//                 Z[e^{i pi/4}] as int64.   (k_pairs: the same with one warp per inner product,
+//                 ballot / shfl / LOP3 / POPC in registers — the first version, kept under BG_KERNEL=warp.)
+//   k_finalize_*  2^t |projfactor * sum|^2 per sample in fp64 and a fixed-order tree sum.
 //
 // There is no CPU fallback anywhere in this file: every entry point either runs the kernels
 // or fails with an error string.
