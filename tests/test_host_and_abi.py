@@ -177,3 +177,45 @@ def test_unmodified_front_end_drives_the_backend():
         assert abs(prob - 0.97855339) < 0.2
     else:
         assert "RUNTIMEERROR" in out and "no CPU fallback" in out
+
+
+def test_bench_host_helpers(monkeypatch):
+    """bench.py's host-side pieces that no GPU run exercises in isolation: the instruction-stream writer is
+    the inverse of the parser (token protocol of libcirc/probability.c:74-127), the synthetic projector only
+    has Hermitian generators, and the clock sampler summarises NVML readings (in-process, fake library here)
+    or falls back to the nvidia-smi poller."""
+    import types
+    import time as _time
+    import bench
+    cfg, G, H, samples, k, _ = bench.load_config("hidden_shift_n40_t16_L16384")
+    text = bench.stream_text(cfg["t"], samples, k, cfg["exact"], G, H)
+    path = os.path.join(ROOT, "tests", "golden", "streams", "hs_t16_bit6.txt")
+    tok_a, tok_b = text.split(), open(path).read().split()
+    assert tok_a[13:] == tok_b[13:]                        # both projectors, token for token
+    assert int(tok_a[5]) == cfg["t"] == 16 and int(tok_a[3]) == samples
+    _, Gs, Hs = bench.synthetic_stream()
+    for (nq, ph, xs, zs) in (Gs, Hs):
+        assert nq == 60 and all((bin(x & z).count("1") - p) % 2 == 0 for p, x, z in zip(ph, xs, zs))
+    assert len(bench.fixed_L(9, 40)) == 9 and bench.fixed_L(9, 40) == bench.fixed_L(9, 40)
+
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, c: 1950
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 4 | 64
+    fake.nvmlClocksEventReasonHwSlowdown, fake.nvmlClocksEventReasonHwThermalSlowdown = 8, 64
+    fake.nvmlClocksEventReasonSwThermalSlowdown, fake.nvmlClocksEventReasonSwPowerCap = 32, 4
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    s = bench.ClockSampler(0)
+    s.start()
+    _time.sleep(0.2)
+    s.stop_flag = True
+    s.join(2)
+    out = s.summary()
+    assert out["source"] == "nvml" and out["sm_mhz"] == 1950 and out["sm_max_mhz"] == 1965 and out["samples"] >= 2
+    assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    broken = types.ModuleType("pynvml")                  # no NVML: the poller of the nvidia-smi binary is used
+    monkeypatch.setitem(sys.modules, "pynvml", broken)
+    assert bench.ClockSampler(0).nvml is None
