@@ -145,6 +145,7 @@ class ClockSampler(threading.Thread):
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)   # static: asked once (1.5 ms a call)
             self.nvml = pynvml
+            self._nvml_row()         # the first call of each query can take tens of ms: pay that here, not in the timed region
         except Exception:
             self.nvml = None
 
