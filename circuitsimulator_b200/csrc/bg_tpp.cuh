@@ -31,7 +31,7 @@
 struct BgWork { unsigned long long xors, rows, dimers, monomers, basis_changes, pairs; };
 extern BgWork g_bg_work;
 #define BG_WORK(field, n) (g_bg_work.field += (n))
-extern int* g_bg_trace; extern int g_bg_trace_n, g_bg_trace_cap;     // per t_xor2 call: |M1|M2| (lo), (hi)
+extern int* g_bg_trace; extern int g_bg_trace_n, g_bg_trace_cap;     // per row pass: 1000 x masks (2, 4, 6) + rows touched in the low half, rows in the high half
 #define BG_TRACE(lo, hi) do { if (g_bg_trace && g_bg_trace_n + 2 <= g_bg_trace_cap) { g_bg_trace[g_bg_trace_n++] = (lo); g_bg_trace[g_bg_trace_n++] = (hi); } } while (0)
 #else
 #define BG_WORK(field, n) ((void)0)
@@ -125,7 +125,7 @@ BG_HD int thighest(uint64_t x) {
 // of a warp close together; words are walked in 32-bit halves from the top bit down (FLO + 2 ops).
 BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2) {
     uint32_t U = M1 | M2;
-    BG_TRACE(tpopc(U), 0);
+    BG_TRACE(2000 + tpopc(U), 0);
 #if defined(__CUDA_ARCH__)
     while (U) {
         const uint32_t c = (uint32_t)thighest(U);
@@ -154,7 +154,7 @@ BG_HD void t_xor2(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
 #endif
 }
 BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2) {
-    BG_TRACE(tpopc((uint32_t)(M1 | M2)), tpopc((uint32_t)((M1 | M2) >> 32)));
+    BG_TRACE(2000 + tpopc((uint32_t)(M1 | M2)), tpopc((uint32_t)((M1 | M2) >> 32)));
 #if defined(__CUDA_ARCH__)
     // Hand-scheduled inner loop (31 % of the kernel's issue slots): per row one FLO, one shift, one
     // IMAD for the shared-memory address, LDS.64, two mask tests, four PREDICATED xors, STS.64.
@@ -204,7 +204,7 @@ BG_HD void t_xor2(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2
 BG_HD void t_xor4(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2,
                   uint32_t M3, uint32_t V3, uint32_t M4, uint32_t V4) {
     uint32_t U = M1 | M2 | M3 | M4;
-    BG_TRACE(tpopc(U), 0);
+    BG_TRACE(4000 + tpopc(U), 0);
 #if defined(__CUDA_ARCH__)
     while (U) {
         const uint32_t c = (uint32_t)thighest(U);
@@ -236,7 +236,7 @@ BG_HD void t_xor4(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
 }
 BG_HD void t_xor4(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2,
                   uint64_t M3, uint64_t V3, uint64_t M4, uint64_t V4) {
-    BG_TRACE(tpopc((uint32_t)(M1 | M2 | M3 | M4)), tpopc((uint32_t)((M1 | M2 | M3 | M4) >> 32)));
+    BG_TRACE(4000 + tpopc((uint32_t)(M1 | M2 | M3 | M4)), tpopc((uint32_t)((M1 | M2 | M3 | M4) >> 32)));
 #if defined(__CUDA_ARCH__)
     const uint32_t v1l = (uint32_t)V1, v1h = (uint32_t)(V1 >> 32), v2l = (uint32_t)V2, v2h = (uint32_t)(V2 >> 32);
     const uint32_t v3l = (uint32_t)V3, v3h = (uint32_t)(V3 >> 32), v4l = (uint32_t)V4, v4h = (uint32_t)(V4 >> 32);
@@ -285,7 +285,7 @@ BG_HD void t_xor4(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2
 BG_HD void t_xor6(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2, uint32_t V2, uint32_t M3, uint32_t V3,
                   uint32_t M4, uint32_t V4, uint32_t M5, uint32_t V5, uint32_t M6, uint32_t V6) {
     uint32_t U = M1 | M2 | M3 | M4 | M5 | M6;
-    BG_TRACE(tpopc(U), 0);
+    BG_TRACE(6000 + tpopc(U), 0);
 #if defined(__CUDA_ARCH__)
     while (U) {
         const uint32_t c = (uint32_t)thighest(U);
@@ -323,7 +323,7 @@ BG_HD void t_xor6(const Rows<uint32_t>& J, uint32_t M1, uint32_t V1, uint32_t M2
 }
 BG_HD void t_xor6(const Rows<uint64_t>& J, uint64_t M1, uint64_t V1, uint64_t M2, uint64_t V2, uint64_t M3, uint64_t V3,
                   uint64_t M4, uint64_t V4, uint64_t M5, uint64_t V5, uint64_t M6, uint64_t V6) {
-    BG_TRACE(tpopc((uint32_t)(M1 | M2 | M3 | M4 | M5 | M6)), tpopc((uint32_t)((M1 | M2 | M3 | M4 | M5 | M6) >> 32)));
+    BG_TRACE(6000 + tpopc((uint32_t)(M1 | M2 | M3 | M4 | M5 | M6)), tpopc((uint32_t)((M1 | M2 | M3 | M4 | M5 | M6) >> 32)));
 #if defined(__CUDA_ARCH__)
     const uint32_t v1l = (uint32_t)V1, v1h = (uint32_t)(V1 >> 32), v2l = (uint32_t)V2, v2h = (uint32_t)(V2 >> 32);
     const uint32_t v3l = (uint32_t)V3, v3h = (uint32_t)(V3 >> 32), v4l = (uint32_t)V4, v4h = (uint32_t)(V4 >> 32);
