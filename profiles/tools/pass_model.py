@@ -30,10 +30,13 @@ if exact:
     terms = [sum(((i >> (size - 1 - j)) & 1) << (2 * j) for j in range(size)) for i in range(1 << size)]
 else:
     terms = [o.Lbits(i, L) for i in range(1 << len(L))]
+# the order the pair kernel uses (bg_set_decomposition): by popcount, then by the popcount of the low half
+terms.sort(key=lambda x: -((bin(x).count("1") << 8) | bin(x & 0xffffffff).count("1")))
 cap = 1 << 22
 buf = (C.c_int * cap)()
 e.lib.emu_trace.argtypes = [C.POINTER(C.c_int), C.c_int]
 pairs = []
+batches = []          # per (sample, 32 consecutive terms): block-rounds of each lane
 for P, seed in ((G, 1001), (H, 1002)):
     for l in range(4 if t > 20 else 16):
         th = o.random_state_philox(t, seed, 0, l)
@@ -43,14 +46,17 @@ for P, seed in ((G, 1001), (H, 1002)):
         e.lib.emu_trace(None, 0)
         if not got["alive"]:
             continue
-        cur = []
+        cur, mine = [], []
         for j in range(0, n, 2):
             lo, hi = buf[j], buf[j + 1]
             if lo == -1:
                 pairs.append(cur)
+                mine.append(cur)
                 cur = []
             else:
                 cur.append((lo // 1000, lo % 1000 + hi))
+        for b in range(0, len(mine), 32):
+            batches.append([sum(1 for k_, r in p if k_ in (4, 6)) for p in mine[b:b + 32]])
 kinds = {2: "parity-check pivot (2 masks)", 6: "first pass of the rounds, with the fold (6 masks)", 4: "two steps (4 masks)"}
 out = {"config": name, "pairs": len(pairs), "per_pair": {}}
 for kind, label in kinds.items():
@@ -61,4 +67,9 @@ for kind, label in kinds.items():
                               "rows_touched": float(np.mean(rows))}
 tot = [sum(1 for k_, r in p if r > 0) for p in pairs]
 out["per_pair"]["all"] = {"passes_touching_rows": float(np.mean(tot)), "rows_touched": float(np.mean([sum(r for _, r in p) for p in pairs]))}
+# lanes of a warp run their block-rounds in lock step: the warp needs max(lane rounds), a lane is busy for its own
+busy = sum(sum(b) for b in batches)
+slots = sum(len(b) * max(b) for b in batches if b)
+out["block_rounds"] = {"per_pair": busy / max(1, len(pairs)), "per_warp_batch_max": float(np.mean([max(b) for b in batches if b])),
+                       "lanes_busy_fraction": busy / max(1, slots)}
 print(json.dumps(out, indent=1))
