@@ -296,8 +296,8 @@ def cpu_baseline_leg(cfgname, seconds=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
