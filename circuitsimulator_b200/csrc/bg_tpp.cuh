@@ -607,7 +607,7 @@ BG_HD void t_block64(const Rows<uint64_t>& J, uint32_t& El, uint32_t& Eh, uint32
 }
 
 BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t& Js, uint32_t& cnt, uint32_t& neg0,
-                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint64_t>& pd64) {
+                    uint32_t& neg1, uint32_t& z0, uint32_t& z1, bool has_s, const TPend<uint64_t>& pd64, bool pending = true) {
     uint32_t El = (uint32_t)E, Eh = (uint32_t)(E >> 32);
     uint32_t D2l = (uint32_t)D2, D2h = (uint32_t)(D2 >> 32), Jsl = (uint32_t)Js, Jsh = (uint32_t)(Js >> 32);
     const uint32_t ns = has_s ? 0u : 1u;
@@ -616,13 +616,12 @@ BG_HD void t_rounds(const Rows<uint64_t>& J, uint64_t& E, uint64_t& D2, uint64_t
     pd.M2l = (uint32_t)pd64.M2; pd.M2h = (uint32_t)(pd64.M2 >> 32); pd.V2l = (uint32_t)pd64.V2; pd.V2h = (uint32_t)(pd64.V2 >> 32);
     // Variables are eliminated from the top, so the high halves die first: once no lane of the warp has a
     // variable >= 32 left, the rounds continue on the low halves of the same rows with 32-bit code.
-    bool pending = true;
 #if defined(__CUDA_ARCH__)
 #define T_ALL_LOW() __all_sync(__activemask(), Eh == 0u)
 #else
 #define T_ALL_LOW() (Eh == 0u)
 #endif
-    if ((El | Eh) != 0u && !T_ALL_LOW()) {
+    if (pending && (El | Eh) != 0u && !T_ALL_LOW()) {
         t_block64<true>(J, El, Eh, D2l, D2h, Jsl, Jsh, cnt, neg0, neg1, z0, z1, ns, pd);
         pending = false;
     }
@@ -683,6 +682,243 @@ template <typename W> BG_HD void t_expsum(const Rows<W>& J, TF<W>& f, int& eps, 
     m = (int)((m0 + (diff == 2u ? 1u : 7u)) & 7u);
 }
 
+
+// =====================================================================================================
+// Odd-first elimination (round 2): the exponential sum without the fold and without the sigma = 0 / 1
+// double bookkeeping of exponentialSumExact (stabilizer.c:300-481); same value, hence the same (eps, p, m mod 8).
+//
+// * A variable a with D_a in {2,6} (D1_a = 1) is summed out on its own:
+//       sum_{x_a} w^{D_a x_a + 4 x_a l(x)} = 1 + i^d (-1)^{l(x)} = sqrt2 w^d i^{-d (l(x) mod 2)},   d = +-1, w = e^{i pi/4}
+//   and l mod 2 = l^2 mod 4, so with v = J_a restricted to the variables left:  Q += d, p += 1, D_c -= 2d for c in v,
+//   J ^= v v^T — a RANK-ONE update whose mask and value are the same word.  With diag(J) = D1 the row update
+//   row_c ^= v (c in v) also flips D1; D2_c ^= (d = +1 ? ~D1_c : D1_c) takes the carry.
+// * K such steps share ONE pass over the rows (t_xork): the pivot row of step j is brought up to date with the
+//   j - 1 earlier steps of its block in registers.  No branch in a block: a step with no odd variable left has
+//   an empty mask.
+// * Only when no variable with D in {2,6} is left does the monomer / dimer elimination (t_rounds, has_s = false)
+//   finish the sum; for a random theta that is the last variable or two.
+// * Parity checks of K_theta need no pivoting here: check j is a Lagrange variable lambda_j with D = 4 beta_j and
+//   row = the check (1/2 sum_lambda (-1)^{lambda (c.x + beta)} = [c.x = beta]); the warp appends these rows and
+//   columns to the ambient form once per sample (k_pairs_tpp) and the term only adds the lambda bits to its
+//   active set; p -= 2 per check.
+// =====================================================================================================
+BG_HD void t_pxor32(uint32_t& r, uint32_t c, uint32_t v) {                    // r ^= v if c != 0
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p xor.b32 %0, %0, %2;\n\t}" : "+r"(r) : "r"(c), "r"(v));
+#else
+    if (c) r ^= v;
+#endif
+}
+BG_HD void t_pxor64(uint32_t& l, uint32_t& h, uint32_t c, uint32_t vl, uint32_t vh) {      // (h:l) ^= (vh:vl) if c != 0
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p xor.b32 %0, %0, %3;\n\t@p xor.b32 %1, %1, %4;\n\t}"
+        : "+r"(l), "+r"(h) : "r"(c), "r"(vl), "r"(vh));
+#else
+    if (c) { l ^= vl; h ^= vh; }
+#endif
+}
+
+// row_c ^= xor of the v_j that contain c, for every row c in U  (32-bit words)
+template <int K> BG_HD void t_xork(const Rows<uint32_t>& J, uint32_t U, const uint32_t (&v)[K]) {
+    BG_TRACE(1000 * K + tpopc(U), 0);
+    while (U) {
+        const uint32_t c = (uint32_t)thighest(U);
+        const uint32_t b = 1u << c;
+        U ^= b;
+#if defined(__CUDA_ARCH__)
+        const uint32_t addr = c * J.sstride + J.sbase;
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+#pragma unroll
+        for (int j = 0; j < K; j++) t_pxor32(r, v[j] & b, v[j]);
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(r) : "memory");
+#else
+        uint32_t r = J.get((int)c);
+        for (int j = 0; j < K; j++) { if (v[j] & b) { r ^= v[j]; BG_WORK(xors, 1); } }
+        J.put((int)c, r);
+        BG_WORK(rows, 1);
+#endif
+    }
+}
+// ... and 64-bit words, as two halves
+template <int K> BG_HD void t_xork(const Rows<uint64_t>& J, uint32_t Ul, uint32_t Uh, const uint32_t (&vl)[K], const uint32_t (&vh)[K]) {
+    BG_TRACE(1000 * K + tpopc(Ul), tpopc(Uh));
+#pragma unroll
+    for (int h = 1; h >= 0; h--) {
+        uint32_t U = h ? Uh : Ul;
+#if defined(__CUDA_ARCH__)
+        const uint32_t hbase = J.sbase + (uint32_t)(32 * h) * J.sstride;
+#endif
+        while (U) {
+            const uint32_t c = (uint32_t)thighest(U);
+            const uint32_t b = 1u << c;
+            U ^= b;
+#if defined(__CUDA_ARCH__)
+            const uint32_t addr = c * J.sstride + hbase;
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+#pragma unroll
+            for (int j = 0; j < K; j++) t_pxor64(lo, hi, (h ? vh[j] : vl[j]) & b, vl[j], vh[j]);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(lo), "r"(hi) : "memory");
+#else
+            uint64_t r = J.get((int)c + 32 * h);
+            for (int j = 0; j < K; j++) { if ((h ? vh[j] : vl[j]) & b) { r ^= t_mk64(vl[j], vh[j]); BG_WORK(xors, 1); } }
+            J.put((int)c + 32 * h, r);
+            BG_WORK(rows, 1);
+#endif
+        }
+    }
+}
+
+// K rank-one steps + one pass (32-bit words)
+template <int K>
+BG_HD void t_oddblock32(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D1, uint32_t& D2, uint32_t& Q, uint32_t& cnt) {
+    uint32_t v[K];
+    uint32_t U = 0u;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const uint32_t O = D1 & E;
+        const bool on = O != 0u;
+        const uint32_t a = (uint32_t)thighest(on ? O : 1u);
+        const uint32_t ba = on ? (1u << a) : 0u;
+        uint32_t r = J.get((int)a);
+#pragma unroll
+        for (int i = 0; i < j; i++) t_pxor32(r, v[i] & ba, v[i]);              // row a as steps < j of this block leave it
+        E &= ~ba;
+        v[j] = on ? (r & E) : 0u;
+        const bool neg = (D2 & ba) != 0u;                                    // D_a = 6: d = -1
+        Q += (on ? 1u : 0u) + (neg ? 6u : 0u);
+        cnt += on ? 1u : 0u;
+        D2 ^= v[j] & (D1 ^ (neg ? 0u : ~0u));
+        D1 ^= v[j];
+        U |= v[j];
+        BG_WORK(monomers, on ? 1 : 0);
+    }
+    t_xork<K>(J, U & E, v);
+}
+
+// K rank-one steps + one pass (64-bit words as halves).  Returns true when the pass was done on the low words
+// only because no lane of the warp has a variable >= 32 left (the caller continues with 32-bit code).
+#if defined(__CUDA_ARCH__)
+#define T_WARP_ALL(x) __all_sync(__activemask(), (x))
+#define T_WARP_ANY(x) __any_sync(__activemask(), (x))
+#else
+#define T_WARP_ALL(x) (x)
+#define T_WARP_ANY(x) (x)
+#endif
+// While a lane has variables >= 32 left the pivot is the TOP variable, odd or not, so that the high halves die
+// within one block: an even top variable a borrows its oddness from a fresh variable mu (D_mu = 2, no
+// couplings, sum_{x_mu} = sqrt2 w — divided out: cnt -= 1, Q -= 1) placed at a FREE low slot f of this term
+// (x_mu = x'_mu + x_a makes a odd and adds bit f to its row; the rank-one step then leaves x'_mu as an even
+// variable with a's couplings).  `fr` = free low slots whose columns are zero in every row (t_copy_in_masked);
+// fr = 0 switches the borrowing off (then: highest odd variable, as in the 32-bit code).
+template <int K>
+BG_HD bool t_oddblock64(const Rows<uint64_t>& J, uint32_t& El, uint32_t& Eh, uint32_t& D1l, uint32_t& D1h, uint32_t& D2l,
+                        uint32_t& D2h, uint32_t& Q, uint32_t& cnt, uint32_t& fr) {
+    uint32_t vl[K], vh[K];
+    uint32_t Ul = 0u, Uh = 0u;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const uint32_t Ol = D1l & El, Oh = D1h & Eh;
+        const bool top = (Eh != 0u) & (fr != 0u);                            // pivot = top variable (it is >= 32)
+        const bool on = top | ((Ol | Oh) != 0u);
+        const TIdx a = t_top64(on ? Ol : 1u, top ? Eh : Oh, J);
+        const uint32_t bl = on ? a.bl : 0u, bh = a.bh;                       // off: the high word is 0, so a.bh = 0
+        uint32_t rl, rh;
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rl), "=r"(rh) : "r"(a.addr));
+#else
+        { const uint64_t r = J.get((int)a.idx); rl = (uint32_t)r; rh = (uint32_t)(r >> 32); }
+#endif
+#pragma unroll
+        for (int i = 0; i < j; i++) t_pxor64(rl, rh, (vl[i] & bl) | (vh[i] & bh), vl[i], vh[i]);
+        const bool ev = top & ((D1h & bh) == 0u);                            // even top variable: borrow from mu at slot f
+        const uint32_t f = (uint32_t)thighest(fr | 1u);
+        const uint32_t fb = ev ? (1u << f) : 0u;
+        if (ev) {
+#if defined(__CUDA_ARCH__)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(f * J.sstride + J.sbase), "r"(fb), "r"(0u) : "memory");
+#else
+            J.put((int)f, (uint64_t)fb);
+#endif
+        }
+        fr &= ~fb;
+        El = (El & ~bl) | fb; Eh &= ~bh;
+        D1l |= fb; D2l &= ~fb;                                               // D_mu = 2
+        vl[j] = on ? ((rl & El) | fb) : 0u; vh[j] = on ? (rh & Eh) : 0u;
+        const bool neg = ((D2l & bl) | (D2h & bh)) != 0u;
+        Q += (on ? 1u : 0u) + (neg ? 6u : 0u) + (ev ? 7u : 0u);
+        cnt += (on ? 1u : 0u) - (ev ? 1u : 0u);
+        const uint32_t dm = neg ? 0u : ~0u;
+        D2l ^= vl[j] & (D1l ^ dm); D2h ^= vh[j] & (D1h ^ dm);
+        D1l ^= vl[j]; D1h ^= vh[j];
+        Ul |= vl[j]; Uh |= vh[j];
+        BG_WORK(monomers, on ? 1 : 0);
+    }
+    if (T_WARP_ALL(Eh == 0u)) {
+        Rows<uint32_t> Jl;                       // the low words of the same rows
+        Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
+        Jl.sbase = J.sbase; Jl.sstride = J.sstride;
+        t_xork<K>(Jl, Ul & El, vl);
+        return true;
+    }
+    t_xork<K>(J, Ul & El, Uh & Eh, vl, vh);
+    return false;
+}
+
+// the steps of the odd phase: blocks of 8 while any lane of the warp has more than 4 variables left
+BG_HD void t_oddphase(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D1, uint32_t& D2, uint32_t& Q, uint32_t& cnt) {
+    while ((D1 & E) != 0u) {
+        if (T_WARP_ANY(tpopc(E) > 4)) t_oddblock32<8>(J, E, D1, D2, Q, cnt);
+        else t_oddblock32<4>(J, E, D1, D2, Q, cnt);
+    }
+}
+
+// sum over F_2^A of e^{i pi q/4}: odd-first.  Same result as t_expsum.
+BG_HD void t_expsum_odd(const Rows<uint32_t>& J, TF<uint32_t>& f, int& eps, int& p, int& m, uint32_t fr = 0u) {
+    (void)fr;
+    uint32_t E = f.A, D1 = f.D1, D2 = f.D2, Q = f.Q, cnt = 0;
+    t_oddphase(J, E, D1, D2, Q, cnt);
+    uint32_t cnt2 = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
+    if (E != 0u) {                                       // what is left has D in {0,4}
+        uint32_t Js = 0;
+        TPend<uint32_t> pd; pd.M1 = pd.V1 = pd.M2 = pd.V2 = 0;
+        t_rounds(J, E, D2, Js, cnt2, neg0, neg1, z0, z1, false, pd, false);
+    }
+    eps = z0 ? 0 : 1;
+    p = (int)cnt + 2 * (int)cnt2;
+    m = (int)((Q + 4u * neg0) & 7u);
+}
+BG_HD void t_expsum_odd(const Rows<uint64_t>& J, TF<uint64_t>& f, int& eps, int& p, int& m, uint32_t fr = 0u) {
+    uint32_t El = (uint32_t)f.A, Eh = (uint32_t)(f.A >> 32), D1l = (uint32_t)f.D1, D1h = (uint32_t)(f.D1 >> 32);
+    uint32_t D2l = (uint32_t)f.D2, D2h = (uint32_t)(f.D2 >> 32), Q = f.Q, cnt = 0;
+    if (tpopc(fr) < tpopc(Eh)) fr = 0u;                  // not enough free low slots: no borrowing for this term
+    bool low = T_WARP_ALL(Eh == 0u);
+    while (!low && ((((D1l & El) | (D1h & Eh)) != 0u) | ((Eh != 0u) & (fr != 0u)))) {
+        if (T_WARP_ANY(tpopc(El) + tpopc(Eh) > 4)) low = t_oddblock64<8>(J, El, Eh, D1l, D1h, D2l, D2h, Q, cnt, fr);
+        else low = t_oddblock64<4>(J, El, Eh, D1l, D1h, D2l, D2h, Q, cnt, fr);
+    }
+    uint32_t cnt2 = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
+    if (Eh == 0u) {                                      // continue on the low words with 32-bit code
+        Rows<uint32_t> Jl;
+        Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
+        Jl.sbase = J.sbase; Jl.sstride = J.sstride;
+        t_oddphase(Jl, El, D1l, D2l, Q, cnt);
+        if (El != 0u) {
+            uint32_t Js = 0;
+            TPend<uint32_t> pd; pd.M1 = pd.V1 = pd.M2 = pd.V2 = 0;
+            t_rounds(Jl, El, D2l, Js, cnt2, neg0, neg1, z0, z1, false, pd, false);
+        }
+    } else {                                             // even variables >= 32 are left and nothing odd: 64-bit rounds
+        uint64_t E = t_mk64(El, Eh), D2 = t_mk64(D2l, D2h), Js = 0;
+        TPend<uint64_t> pd; pd.M1 = pd.V1 = pd.M2 = pd.V2 = 0;
+        t_rounds(J, E, D2, Js, cnt2, neg0, neg1, z0, z1, false, pd, false);
+    }
+    eps = z0 ? 0 : 1;
+    p = (int)cnt + 2 * (int)cnt2;
+    m = (int)((Q + 4u * neg0) & 7u);
+}
+
 // What a warp shares about its theta: the ambient form and at most TPP_MAXC parity checks.
 #define TPP_MAXC 6
 template <typename W> struct TShared {
@@ -690,7 +926,8 @@ template <typename W> struct TShared {
     W D1, D2;
     uint32_t Q;
     int k1, t;
-    int ncons;           // parity checks (t - k1)
+    int ncons;           // parity checks (t - k1) that the term has to pivot
+    int nlam;            // parity checks carried as Lagrange variables t .. t+nlam-1 of the ambient form (then ncons = 0)
     W cw[TPP_MAXC];      // the checks when ncons <= TPP_MAXC (register copy)
     uint32_t cbeta;      // bit j = right-hand side of check j (ncons <= TPP_MAXC)
     const W* cwv;        // all checks (shared memory) and their right-hand sides, any ncons <= t
@@ -752,10 +989,12 @@ BG_HD bool t_constraints_many(const Rows<W>& J, TF<W>& f, const TShared<W>& sh, 
 }
 
 // the thread's working copy of the ambient J.  Device: the warp's ambient rows are 16-byte aligned
-// (k_pairs_tpp pads them), so they are read with 128-bit broadcast loads.
+// (k_pairs_tpp pads them), so they are read with 128-bit broadcast loads.  `keep`: mask applied to the low
+// 32 columns (64-bit words only): columns of inactive variables are cleared so that they can serve as free
+// slots (t_oddblock64).
 template <typename W>
-BG_HD void t_copy_in(const Rows<W>& J, const TShared<W>& sh) {
-    const int t = sh.t;
+BG_HD void t_copy_in(const Rows<W>& J, const TShared<W>& sh, uint32_t keep = ~0u) {
+    const int t = sh.t + sh.nlam;
 #if defined(__CUDA_ARCH__)
     const uint32_t amb = (uint32_t)__cvta_generic_to_shared(sh.J);
     constexpr int PER = 16 / (int)sizeof(W);
@@ -765,14 +1004,14 @@ BG_HD void t_copy_in(const Rows<W>& J, const TShared<W>& sh) {
         uint32_t x0, x1, x2, x3;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(amb + (uint32_t)q * (uint32_t)sizeof(W)));
         if (sizeof(W) == 8) {
-            J.put(q, (W)(((uint64_t)x1 << 32) | x0)); J.put(q + 1, (W)(((uint64_t)x3 << 32) | x2));
+            J.put(q, (W)(((uint64_t)x1 << 32) | (x0 & keep))); J.put(q + 1, (W)(((uint64_t)x3 << 32) | (x2 & keep)));
         } else {
             J.put(q, (W)x0); J.put(q + 1, (W)x1); J.put(q + 2, (W)x2); J.put(q + 3, (W)x3);
         }
     }
-    for (; q < t; q++) J.put(q, sh.J[q]);
+    for (; q < t; q++) J.put(q, sizeof(W) == 8 ? (W)(sh.J[q] & ((W)~(W)0xffffffffu | keep)) : sh.J[q]);
 #else
-    for (int q = 0; q < t; q++) J.put(q, sh.J[q]);
+    for (int q = 0; q < t; q++) J.put(q, sizeof(W) == 8 ? (W)(sh.J[q] & ((W)~(W)0xffffffffu | keep)) : sh.J[q]);
 #endif
 }
 
@@ -780,14 +1019,21 @@ BG_HD void t_copy_in(const Rows<W>& J, const TShared<W>& sh) {
 template <typename W, bool MANYC = false>
 BG_HD void t_term_L(const Rows<W>& J, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
     const int t = sh.t;
-    t_copy_in<W>(J, sh);
     TF<W> f;
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
     f.A = xt & tlowmask<W>(t);
     const int k2 = tpopc(f.A);
+    // low columns of the variables that are not in the term are cleared: free slots for t_oddblock64
+    const uint32_t fr = (sizeof(W) == 8 && !MANYC && sh.ncons == 0) ? ~(uint32_t)f.A : 0u;
+    t_copy_in<W>(J, sh, ~fr);
     if (!(MANYC ? t_constraints_many<W>(J, f, sh, (W)0) : t_constraints<W>(J, f, sh, (W)0))) { eps = 0; p = 0; m = 0; return; }
+    f.A |= tlowmask<W>(sh.nlam) << (sh.nlam ? t : 0);            // the Lagrange variables of the parity checks
+#if defined(BG_ELIM_FOLD)
     t_expsum<W>(J, f, eps, p, m);
-    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
+#else
+    t_expsum_odd(J, f, eps, p, m, fr);
+#endif
+    if (eps) p -= sh.k1 + k2 + 2 * sh.nlam; else { p = 0; m = 0; }
 }
 
 // <phi|theta> for a |H^t> term (prepH); e1 as in bg_device.cuh: term_H.
@@ -802,7 +1048,8 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
     for (int q = 0; q < t; q++) J.put(q, sh.J[q] ^ (((cz2 >> q) & 1) ? tbit<W>(q ^ 1) : (W)0));     // q1 - q2
     TF<W> f;
     f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
-    f.A = maskt & ~last;
+    f.A = (maskt & ~last) | (tlowmask<W>(sh.nlam) << (sh.nlam ? t : 0));     // + the Lagrange variables of the checks
+    for (int q = t; q < t + sh.nlam; q++) J.put(q, sh.J[q]);
     for (W r = mrg; r; r &= r - 1) {                    // x_{2j} = x_{2j+1}: eliminate x_{2j}
         const int i = tlowest(r);
         t_basis_change<W>(J, f, i, tbit<W>(i + 1));
@@ -810,166 +1057,12 @@ BG_HD void t_term_H(const Rows<W>& J, const TShared<W>& sh, W e1, int& eps, int&
     }
     const int k2 = t - tpopc(mrg) - tpopc(last);
     if (!(MANYC ? t_constraints_many<W>(J, f, sh, mrg) : t_constraints<W>(J, f, sh, mrg))) { eps = 0; p = 0; m = 0; return; }
+#if defined(BG_ELIM_FOLD)
     t_expsum<W>(J, f, eps, p, m);
-    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
-}
-
-// ---------------------------------------------------------------- left-looking ("lazy") variant
-// The eager routines above update every remaining row of J after each elimination step; the trip
-// counts of those row loops differ from lane to lane (ncu: 20.8 of 32 lanes active), and each touched
-// row costs an LDS + STS + loop overhead.  Every update has the form
-//        row_c ^= [c in M1] V1 ^ [c in M2] V2        with masks that do not depend on the row,
-// so instead of applying it to all rows we only REMEMBER (M1,V1,M2,V2) and materialise a row when it
-// becomes a pivot:  row_c = ambient_c ^ (all remembered updates whose mask contains c).  Per round two
-// rows are materialised, each with a loop over the history whose length is the round number — the
-// SAME for all lanes of a warp.  No per-thread copy of J exists at all; the thread's shared-memory
-// rows hold the dimer history (two words per dimer, at most t/2 dimers).
-// Used for |L> terms with at most LZ_MAXB - 1 parity checks; everything else takes the eager path.
-// Measured (B200, round 1): against the eager kernel as first committed 5.32 vs 5.78 ms at t = 60 but
-// 5.92 vs 4.67 ms at t = 40; against the blocked eager rounds above it loses everywhere (t = 60, k = 12:
-// 149 vs 109 ms) — the blocked passes remove most of the divergence it was meant to avoid.  Kept as an
-// option (BG_LAZY=1) and as a cross-check of the eager path in the test-suite, not the default.
-#define LZ_MAXB 5                      // basis changes kept in registers: up to 4 check pivots + the fold
-template <typename W> struct LzBC { W Sp, Ji, col; };
-
-template <typename W>
-BG_HD W lz_row(const TShared<W>& sh, int c, const LzBC<W> (&bc)[LZ_MAXB], int nb, const Rows<W>& H, int r) {
-    W row = sh.J[c];
-    const W bc_ = tbit<W>(c);
-#pragma unroll
-    for (int j = 0; j < LZ_MAXB; j++) {
-        if (j < nb) {
-            if (bc[j].Sp & bc_) row ^= bc[j].Ji;
-            if (bc[j].col & bc_) row ^= bc[j].Sp;
-        }
-    }
-    for (int q = 0; q < r; q++) {
-        const W X = H.get(2 * q), Y = H.get(2 * q + 1);
-        if (X & bc_) row ^= Y;
-        if (Y & bc_) row ^= X;
-    }
-    BG_WORK(rows, 1); BG_WORK(xors, r);
-    return row;
-}
-
-// x_i = x'_i + sum_{a in Sp} x'_a, remembered instead of applied (cf. t_basis_change)
-template <typename W>
-BG_HD W lz_basis_change(const TShared<W>& sh, TF<W>& f, int i, W Sp, LzBC<W> (&bc)[LZ_MAXB], int& nb, const Rows<W>& H) {
-    const W bi = tbit<W>(i);
-    const W Ji = lz_row<W>(sh, i, bc, nb, H, 0);
-    const W col = (Ji ^ ((Ji & bi) ? Sp : (W)0)) & f.A;
-#pragma unroll
-    for (int j = 0; j < LZ_MAXB; j++) if (j == nb) { bc[j].Sp = Sp; bc[j].Ji = Ji; bc[j].col = col; }
-    nb++;
-    const W d1i = tfill<W>(tget(f.D1, i)), d2i = tfill<W>(tget(f.D2, i));
-    f.D2 ^= Sp & (d2i ^ (d1i & f.D1) ^ Ji);
-    f.D1 ^= Sp & d1i;
-    BG_WORK(basis_changes, 1);
-    return Ji;
-}
-
-template <typename W>
-BG_HD void lz_pivot(const TShared<W>& sh, TF<W>& f, W S, uint32_t beta, LzBC<W> (&bc)[LZ_MAXB], int& nb, const Rows<W>& H) {
-    const int i = thighest(S);
-    const W bi = tbit<W>(i), Sp = S ^ bi;
-    const uint32_t d1 = tget(f.D1, i), d2 = tget(f.D2, i);
-    const W Ji = lz_basis_change<W>(sh, f, i, Sp, bc, nb, H);
-    if (beta) {
-        f.Q = (f.Q + 2u * d1 + 4u * d2) & 7u;
-        f.D2 ^= Ji ^ (Sp & tfill<W>(d1));
-    }
-    f.A &= ~bi;
-}
-
-// <phi|theta> for a |L> term, left-looking.  H: the thread's scratch rows (>= t words).
-// Requires sh.ncons <= LZ_MAXB - 1.
-template <typename W>
-BG_HD void t_term_L_lazy(const Rows<W>& H, const TShared<W>& sh, W xt, int& eps, int& p, int& m) {
-    const int t = sh.t;
-    TF<W> f;
-    f.D1 = sh.D1; f.D2 = sh.D2; f.Q = sh.Q;
-    f.A = xt & tlowmask<W>(t);
-    const int k2 = tpopc(f.A);
-    LzBC<W> bc[LZ_MAXB];
-    int nb = 0;
-    // parity checks (cf. t_constraints): earlier pivots are substituted lazily
-    {
-        W hs[LZ_MAXB - 1];
-        uint32_t hb = 0;
-#pragma unroll
-        for (int j = 0; j < LZ_MAXB - 1; j++) {
-            if (j >= sh.ncons) break;
-            W w = sh.cw[j];
-            uint32_t beta = (sh.cbeta >> j) & 1u;
-#pragma unroll
-            for (int q = 0; q < LZ_MAXB - 1; q++) {
-                if (q >= j) break;
-                if (hs[q] && tget(w, thighest(hs[q]))) { w ^= hs[q]; beta ^= (hb >> q) & 1u; }
-            }
-            w &= f.A;
-            hs[j] = w;
-            hb |= beta << j;
-            if (w == 0) { if (beta) { eps = 0; p = 0; m = 0; return; } continue; }
-            lz_pivot<W>(sh, f, w, beta, bc, nb, H);
-        }
-    }
-    // exponential sum (cf. t_expsum / t_rounds)
-    const W A = f.A;
-    const W S = f.D1 & A;
-    const bool has_s = S != 0;
-    W E = A, Js = 0;
-    uint32_t Ds = 0;
-    if (has_s) {
-        const int s = thighest(S);
-        const W bs = tbit<W>(s), Sp = S ^ bs;
-        Ds = 2u + 4u * tget(f.D2, s);
-        if (Sp) lz_basis_change<W>(sh, f, s, Sp, bc, nb, H);
-        E = A & ~bs;
-        Js = lz_row<W>(sh, s, bc, nb, H, 0) & E;
-    }
-    W D2 = f.D2;
-    uint32_t cnt = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
-    int r = 0;
-    while (E) {
-        const int a = thighest(E);
-        const W ba = tbit<W>(a);
-        const W Ja = lz_row<W>(sh, a, bc, nb, H, r) & E & ~ba;
-        const uint32_t d2a = tget(D2, a), sa = tget(Js, a);
-        if (Ja == 0) {
-            z0 |= d2a; z1 |= d2a ^ sa; cnt++;
-            E ^= ba;
-            BG_WORK(monomers, 1);
-            if (z0 && (z1 || !has_s)) break;
-            continue;
-        }
-        const int b = thighest(Ja);
-        const W bb = tbit<W>(b);
-        const W Jb = lz_row<W>(sh, b, bc, nb, H, r) & E & ~bb;
-        const W rest = E & ~(ba | bb);
-        const uint32_t d2b = tget(D2, b), sb = tget(Js, b);
-        neg0 ^= d2a & d2b; neg1 ^= (d2a ^ sa) & (d2b ^ sb); cnt++;
-        const W Jar = Ja & rest, Jbr = Jb & rest;
-        BG_WORK(dimers, 1);
-        H.put(2 * r, Jar); H.put(2 * r + 1, Jbr);                      // remember: row_c ^= [Jar_c] Jbr ^ [Jbr_c] Jar
-        r++;
-        D2 ^= (Jar & tfill<W>(d2b)) ^ (Jbr & tfill<W>(d2a)) ^ (Jar & Jbr);
-        Js ^= (Jar & tfill<W>(sb)) ^ (Jbr & tfill<W>(sa));
-        E = rest;
-    }
-    p = 2 * (int)cnt;
-    const uint32_t m0 = (f.Q + 4u * neg0) & 7u;
-    if (!has_s) { eps = z0 ? 0 : 1; m = (int)m0; }
-    else {
-        const uint32_t m1 = (f.Q + Ds + 4u * neg1) & 7u;
-        if (z0 && z1) { eps = 0; }
-        else {
-            eps = 1;
-            if (z0) m = (int)m1;
-            else if (z1) m = (int)m0;
-            else { p += 1; m = (int)((m0 + ((((m1 - m0) & 7u) == 2u) ? 1u : 7u)) & 7u); }
-        }
-    }
-    if (eps) p -= sh.k1 + k2; else { p = 0; m = 0; }
+#else
+    t_expsum_odd(J, f, eps, p, m);
+#endif
+    if (eps) p -= sh.k1 + k2 + 2 * sh.nlam; else { p = 0; m = 0; }
 }
 
 }  // namespace bg

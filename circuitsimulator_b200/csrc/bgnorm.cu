@@ -103,7 +103,8 @@ struct PairArgs {
     uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
-    int lazy;                                  // |L> terms with few parity checks: left-looking elimination (bg_tpp.cuh)
+    int lam_max;                               // samples with at most this many parity checks carry them as Lagrange
+                                               // variables t .. t+lam_max-1 of the ambient form (t + lam_max <= word size)
 };
 
 // work item -> (sample index, term range)
@@ -303,10 +304,13 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
     return (long long)(((unsigned long long)hi << 32) | lo);
 }
 
-// ambient rows per warp (+ the check rows when MANYC), padded to a multiple of 4 words: 16-byte aligned
-__host__ __device__ __forceinline__ int tpp_amb_rows(int t, bool manyc) { return ((manyc ? 2 * t : t) + 3) & ~3; }
+// ambient rows per warp (+ the Lagrange rows of the checks, or all check rows when MANYC), padded to a
+// multiple of 4 words: 16-byte aligned
+__host__ __device__ __forceinline__ int tpp_amb_rows(int t, int lam_max, bool manyc) { return ((manyc ? 2 * t : t + lam_max) + 3) & ~3; }
+// working rows per thread
+__host__ __device__ __forceinline__ int tpp_work_rows(int t, int lam_max, bool manyc) { return manyc ? 2 * t : t + lam_max; }
 
-template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
+template <typename W, bool EXACT, bool TRI, bool MANYC>
 __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
     const int t = a.t;
     if (MANYC && *a.n_warp_routed == 0ull) return;      // nothing has more than TPP_MAXC parity checks
     // per warp: t ambient rows (+ t check rows when MANYC); per thread: t working rows (+ t history rows)
-    const int amb_rows = tpp_amb_rows(t, MANYC);
+    const int amb_rows = tpp_amb_rows(t, a.lam_max, MANYC);
     uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
     W* s_amb = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + warp * amb_rows;
     W* s_rows = reinterpret_cast<W*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * amb_rows + threadIdx.x;
@@ -339,10 +343,10 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
         const int diag_index = TRI ? (int)(a.first + (uint64_t)idx * a.stride) : -1;
         if (i0 >= i1) continue;
         __syncwarp();
-        for (int q = lane; q < t; q += 32) s_amb[q] = (W)r->J[q];
+        if (MANYC) for (int q = lane; q < t; q += 32) s_amb[q] = (W)r->J[q];
         TShared<W> sh;
         sh.J = s_amb; sh.D1 = (W)r->D1; sh.D2 = (W)r->D2; sh.Q = (uint32_t)r->Q; sh.k1 = r->k1; sh.t = t;
-        sh.ncons = 0; sh.cbeta = 0; sh.cwv = s_amb + t; sh.cbetav = 0;
+        sh.ncons = 0; sh.nlam = 0; sh.cbeta = 0; sh.cwv = s_amb + t; sh.cbetav = 0;
         if (MANYC) {                      // compact the check rows into shared memory, in row order
             const uint64_t pend = r->Cpend, cbeta = r->Cbeta;
             for (int q = lane; q < t; q += 32)
@@ -369,9 +373,24 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
                     sh.ncons = j + 1;
                 }
             }
+            // few checks: append them to the ambient form as Lagrange variables t .. t+nlam-1 (bg_tpp.cuh)
+            const bool lam = sh.ncons <= a.lam_max;
+            for (int q = lane; q < t; q += 32) {
+                W row = (W)r->J[q];
+                if (lam) {
+#pragma unroll
+                    for (int j = 0; j < TPP_MAXC; j++) row |= (W)((sh.cw[j] >> q) & 1) << ((t + j) & (8 * (int)sizeof(W) - 1));
+                }
+                s_amb[q] = row;
+            }
+            if (lam) {
+#pragma unroll
+                for (int j = 0; j < TPP_MAXC; j++) if (j < sh.ncons && lane == j) s_amb[t + j] = sh.cw[j];
+                sh.D2 |= (W)sh.cbeta << t;
+                sh.nlam = sh.ncons; sh.ncons = 0;
+            }
         }
         __syncwarp();
-        const bool use_lazy = LAZY && !EXACT && !MANYC && sh.ncons <= LZ_MAXB - 1;     // warp-uniform
         Zw z, z2;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
@@ -383,7 +402,6 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
                 const W term = (W)terms[i];
                 int e, p, m;
                 if (EXACT) t_term_H<W, MANYC>(rows, sh, term, e, p, m);
-                else if (LAZY && use_lazy) t_term_L_lazy<W>(rows, sh, term, e, p, m);
                 else t_term_L<W, MANYC>(rows, sh, term, e, p, m);
                 __syncwarp(group);          // the lanes leave the elimination at different times: accumulate together
                 if (TRI && nat != diag_index) zw_add(z2, e, p, m, sh_);
@@ -597,7 +615,11 @@ struct bg_ctx {
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
     int ctas_per_sm = 8, items_factor = 8;
-    int lazy = 0;                   // BG_LAZY=1: left-looking elimination for |L> terms (slower than the blocked eager rounds; kept as a cross-check)
+#if defined(BG_ELIM_FOLD)
+    int lam_max = 0;
+#else
+    int lam_max = 4;
+#endif                          // BG_LAM_MAX: parity checks carried as Lagrange variables (0: pivot every check per term)
     const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
@@ -704,7 +726,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     cudaMemset(ctx->d_ticket, 0, 2 * sizeof(unsigned int));
     cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
-    if (const char* e6 = getenv("BG_LAZY")) ctx->lazy = atoi(e6) != 0;
+    if (const char* e6 = getenv("BG_LAM_MAX")) ctx->lam_max = std::max(0, std::min(TPP_MAXC, atoi(e6)));
     if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
@@ -951,25 +973,24 @@ template <int NS, bool EXACT> static int launch_pairs_ns(bg_ctx* ctx, const Pair
     return 0;
 }
 
-template <typename W, bool EXACT, bool TRI, bool MANYC, bool LAZY>
+template <typename W, bool EXACT, bool TRI, bool MANYC>
 static int launch_tpp_inst(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
     if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_pairs_tpp<W, EXACT, TRI, MANYC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: exactly the CTAs that are resident at once (a multiple of the SM count), fewer if
     // there are not that many work items
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY>, 32 * ctx->tpp_warps, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_tpp<W, EXACT, TRI, MANYC>, 32 * ctx->tpp_warps, smem));
     if (per_sm < 1) return fail(ctx, "k_pairs_tpp: a CTA of %d warps with %zu bytes of shared memory does not fit an SM", ctx->tpp_warps, smem);
     blocks = std::min(blocks, ctx->sm_count * per_sm);
-    k_pairs_tpp<W, EXACT, TRI, MANYC, LAZY><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
+    k_pairs_tpp<W, EXACT, TRI, MANYC><<<blocks, 32 * ctx->tpp_warps, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     return 0;
 }
 template <typename W, bool MANYC> static int launch_tpp_w(bg_ctx* ctx, const PairArgs& a, int blocks, size_t smem) {
-    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true, MANYC, false>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false, MANYC, false>(ctx, a, blocks, smem);
-    if (!MANYC && ctx->lazy && !a.tri) return launch_tpp_inst<W, false, false, false, true>(ctx, a, blocks, smem);
-    return a.tri ? launch_tpp_inst<W, false, true, MANYC, false>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false, MANYC, false>(ctx, a, blocks, smem);
+    if (ctx->exact) return a.tri ? launch_tpp_inst<W, true, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, true, false, MANYC>(ctx, a, blocks, smem);
+    return a.tri ? launch_tpp_inst<W, false, true, MANYC>(ctx, a, blocks, smem) : launch_tpp_inst<W, false, false, MANYC>(ctx, a, blocks, smem);
 }
 
 // Fill in chunking / staging and launch the pair kernels: k_pairs_tpp for the samples routed to it,
@@ -1002,7 +1023,6 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     a.n_warp_routed = cnt + 2;
     a.terms = ctx->d_terms_sorted;
     a.term_nat = ctx->d_term_nat;
-    a.lazy = ctx->lazy;
     if (!ctx->force_warp) {
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;
@@ -1013,11 +1033,13 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         if (tb < 1) tb = 1;
         // samples with <= TPP_MAXC parity checks, then (returns at once if there are none) the rest
         a.counter = cnt;
-        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, false) * wb + (size_t)a.t * 32 * tw * wb;
+        a.lam_max = std::max(0, std::min(ctx->lam_max, (int)(8 * wb) - a.t));
+        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, a.lam_max, false) * wb
+                      + (size_t)tpp_work_rows(a.t, a.lam_max, false) * 32 * tw * wb;
         if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
         else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
         a.counter = cnt + 3;
-        smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, true) * wb + 2 * (size_t)a.t * 32 * tw * wb;
+        smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, 0, true) * wb + (size_t)tpp_work_rows(a.t, 0, true) * 32 * tw * wb;
         if (a.t <= 32) return launch_tpp_w<uint32_t, true>(ctx, a, (int)tb, smem);
         return launch_tpp_w<uint64_t, true>(ctx, a, (int)tb, smem);
     }

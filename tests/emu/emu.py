@@ -58,8 +58,9 @@ class Emu:
         return tuple(out)
 
     def terms(self, theta, P, project, exact, t, terms, tpp=False):
-        """tpp=True: the chi loop through the thread-per-pair code; tpp="lazy": its left-looking variant."""
-        self.lib.emu_set_lazy(1 if tpp == "lazy" else 0)
+        """tpp=True: the chi loop through the thread-per-pair code (parity checks as Lagrange variables, as
+        k_pairs_tpp stages them); tpp="pivot": the same with every check pivoted per term (BG_LAM_MAX=0)."""
+        self.lib.emu_set_lam_max(0 if tpp == "pivot" else 4)
         n = len(terms)
         epm = np.zeros((n, 3), dtype=np.int32)
         npf, k = C.c_int(), C.c_int()

@@ -6,6 +6,7 @@
 #include "bg_warp_ops.cuh"
 #include "bg_tpp.cuh"
 #include <string.h>
+#include <algorithm>
 
 namespace emu {
 thread_local Warp* g_warp = nullptr;
@@ -48,7 +49,7 @@ BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
 int* g_bg_trace = nullptr; int g_bg_trace_n = 0, g_bg_trace_cap = 0;
 using namespace bg;
 
-static int g_emu_lazy = 0;      // 1: use the left-looking variant where the device would
+static int g_emu_lam_max = 4;   // checks carried as Lagrange variables (as k_pairs_tpp does; 0: every check pivoted per term)
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
 // ambient form is produced by the warp-level code under emulation, each term is then a plain call.
 template <int NS>
@@ -75,7 +76,8 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
     if (alive) {
         TShared<W> sh;
         W cwv[64];
-        sh.J = Jrows; sh.D1 = D1; sh.D2 = D2; sh.Q = Q; sh.k1 = k1; sh.t = t; sh.ncons = 0; sh.cbeta = 0;
+        W amb[2 * 64];
+        sh.J = amb; sh.D1 = D1; sh.D2 = D2; sh.Q = Q; sh.k1 = k1; sh.t = t; sh.ncons = 0; sh.nlam = 0; sh.cbeta = 0;
         sh.cwv = cwv; sh.cbetav = 0;
         for (int j = 0; j < TPP_MAXC; j++) sh.cw[j] = 0;
         for (W r = Cpend; r; r &= r - 1) {
@@ -86,13 +88,20 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
             sh.ncons++;
         }
         const bool many = sh.ncons > TPP_MAXC;      // the device routes these to the MANYC instantiation
+        for (int q = 0; q < t; q++) amb[q] = Jrows[q];
+        const int lam_max = std::max(0, std::min(g_emu_lam_max, (int)(8 * sizeof(W)) - t));
+        if (!many && sh.ncons <= lam_max) {         // as k_pairs_tpp: the checks become Lagrange variables t .. t+nlam-1
+            for (int q = 0; q < t; q++)
+                for (int j = 0; j < sh.ncons; j++) amb[q] |= (W)((sh.cw[j] >> q) & 1) << (t + j);
+            for (int j = 0; j < sh.ncons; j++) amb[t + j] = sh.cw[j];
+            sh.D2 |= (W)sh.cbeta << t;
+            sh.nlam = sh.ncons; sh.ncons = 0;
+        }
         W work[128];
         Rows<W> rows; rows.base = work; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
-            if (g_emu_lazy && !exact && sh.ncons <= LZ_MAXB - 1) {
-                t_term_L_lazy<W>(rows, sh, (W)terms[i], e, p, m);
-            } else if (many) {
+            if (many) {
                 if (exact) t_term_H<W, true>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, true>(rows, sh, (W)terms[i], e, p, m);
             } else {
                 if (exact) t_term_H<W, false>(rows, sh, (W)terms[i], e, p, m); else t_term_L<W, false>(rows, sh, (W)terms[i], e, p, m);
@@ -137,7 +146,7 @@ int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int
     return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
 }
 
-void emu_set_lazy(int on) { g_emu_lazy = on; }
+void emu_set_lam_max(int n) { g_emu_lam_max = n; }
 void emu_trace(int* buf, int cap) { g_bg_trace = buf; g_bg_trace_cap = cap; g_bg_trace_n = 0; }
 int emu_trace_len(void) { return g_bg_trace_n; }
 

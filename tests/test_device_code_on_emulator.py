@@ -67,7 +67,7 @@ def _terms(cfg, L, oracle):
     return [oracle.Lbits(i, L) for i in range(1 << len(L))]
 
 
-@pytest.mark.parametrize("tpp", [False, True, "lazy"], ids=["warp_per_pair", "thread_per_pair", "thread_per_pair_lazy"])
+@pytest.mark.parametrize("tpp", [False, True, "pivot"], ids=["warp_per_pair", "thread_per_pair", "thread_per_pair_pivoted_checks"])
 @pytest.mark.parametrize("stream,k,ns", [("htstack_t4.txt", 0, 24), ("hs_t16_bit6.txt", 0, 3),
                                          ("hs_t40_k9_bit0.txt", 5, 3), ("phase_estimation_q0.txt", 4, 3),
                                          ("toffoli_q0.txt", 0, 2)])
