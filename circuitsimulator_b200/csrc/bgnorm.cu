@@ -33,6 +33,7 @@
 #include "bg_philox.cuh"
 #include "bg_warp_ops.cuh"
 #include "bg_tpp.cuh"
+#include "bg_shb.cuh"
 
 using namespace bg;
 
@@ -49,7 +50,8 @@ using namespace bg;
 // alive: 0 = annihilated by the projector; ROUTE_TPP / ROUTE_TPP_MANY = evaluated by k_pairs_tpp (one
 // thread per inner product; _MANY: more than TPP_MAXC parity checks, pivot history in shared memory);
 // ROUTE_WARP = evaluated by k_pairs (one warp per inner product; only under BG_KERNEL=warp).
-enum { ROUTE_DEAD = 0, ROUTE_TPP = 1, ROUTE_WARP = 2, ROUTE_TPP_MANY = 3 };
+// ROUTE_SHB = evaluated by k_pairs_shb (shared high-block reduction, bg_shb.cuh; at most SHB_MAXLAM parity checks).
+enum { ROUTE_DEAD = 0, ROUTE_TPP = 1, ROUTE_WARP = 2, ROUTE_TPP_MANY = 3, ROUTE_SHB = 4 };
 struct SampleRec {          // one projected theta in ambient form (see bg_device.cuh: ambient())
     int32_t alive, k1, npf, Q;
     uint64_t D1, D2, Cpend, Cbeta;
@@ -79,6 +81,7 @@ struct PrepArgs {
     bg_state* raw_out; uint64_t* raw_A;
     long long* zw; long long* zw2;      // per-sample accumulators, zeroed here (zw2 may be null)
     int force_warp;                     // route every sample to the warp-per-pair kernel
+    int shb;                            // the decomposition has a shared high-block plan: samples with few checks -> ROUTE_SHB
     unsigned long long* n_warp_routed;  // device counter: samples NOT taken by the plain k_pairs_tpp
 };
 
@@ -103,6 +106,7 @@ struct PairArgs {
     uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
+    ShbPerm shb;                               // k_pairs_shb: the relabelling of the variables (bg_shb_plan.h)
     int lam_max;                               // samples with at most this many parity checks carry them as Lagrange
                                                // variables t .. t+lam_max-1 of the ambient form (t + lam_max <= word size)
 };
@@ -184,8 +188,11 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
             continue;
         }
         if (lane == 0) {
-            const int route = a.force_warp ? ROUTE_WARP : (popcw(am.Cpend) > TPP_MAXC ? ROUTE_TPP_MANY : ROUTE_TPP);
-            if (route != ROUTE_TPP) atomicAdd(a.n_warp_routed, 1ull);
+            const int nchk = popcw(am.Cpend);
+            const int route = a.force_warp ? ROUTE_WARP
+                              : a.shb ? (nchk > SHB_MAXLAM ? ROUTE_TPP_MANY : ROUTE_SHB)
+                                      : (nchk > TPP_MAXC ? ROUTE_TPP_MANY : ROUTE_TPP);
+            if (route != ROUTE_TPP && route != ROUTE_SHB) atomicAdd(a.n_warp_routed, 1ull);
             r->alive = route; r->k1 = am.k1; r->npf = npf; r->Q = (int32_t)am.f.Q;
             r->D1 = (uint64_t)am.f.D1; r->D2 = (uint64_t)am.f.D2;
             r->Cpend = (uint64_t)am.Cpend; r->Cbeta = (uint64_t)am.Cbeta;
@@ -433,6 +440,92 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
     if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_pairs_shb: the L x chi loop for 32 < t <= 44 with a shared high-block plan (bg_shb.cuh).  One thread per
+// inner product, a warp = one theta x 32 terms that agree on the variables >= 32: the warp sums those out once
+// per batch (shb_reduce), every thread then eliminates a form on <= 32 variables in 32-bit words.
+// dynamic smem: [staged terms][per warp: 32 reduced rows + SHB_MAXHT leftover rows][working rows: 32 x blockDim words]
+// ------------------------------------------------------------------------------------------
+#define SHB_WARP_WORDS (32 + SHB_MAXHT)
+__global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int lane = bg_lane(), warp = threadIdx.x >> 5;
+    constexpr int nwarps = BG_TPP_WARPS;
+    const int t = a.t;
+    uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* s_red = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.smem_terms * 8) + warp * SHB_WARP_WORDS;
+    uint32_t* s_left = s_red + 32;
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * SHB_WARP_WORDS + threadIdx.x;
+    if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
+    const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
+    Rows<uint32_t> rows; rows.base = s_rows; rows.stride = BG_TPP_THREADS;
+    rows.sbase = smem_u32(s_rows); rows.sstride = BG_TPP_THREADS * 4u;
+
+    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
+    const int sh_ = t / 2 + 1;
+    unsigned long long my_pairs = 0;
+    while (true) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.counter, 1ull);
+        item = __shfl_sync(BG_FULL, item, 0);
+        if (item >= n_items) break;
+        int idx, i0, i1;
+        item_range(a, item, idx, i0, i1);
+        const SampleRec* r = &a.recs[idx];
+        if (r->alive != ROUTE_SHB) continue;
+        if (i0 >= i1) continue;
+        ShbForm f;
+        const int nlam = shb_load(r->J, r->Cw, r->Cpend, r->Cbeta, r->D1, r->D2, (uint32_t)r->Q, t, a.shb, f);
+        const int k1 = r->k1;
+        const uint32_t lam_bits = ((1u << nlam) - 1u) << a.shb.nh;
+        Zw z;
+        z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+        for (int g = i0; g < i1; g += 32) {                     // every batch of 32 terms has one high pattern
+            const uint64_t term = terms[g + lane];
+            const uint32_t pattern = __shfl_sync(BG_FULL, (uint32_t)(term >> 32), 0);
+            ShbOut o; uint32_t Lr, Rr;
+            shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
+            __syncwarp();
+            s_red[lane] = Lr;
+            ShbBatch sb;
+            sb.red = s_red; sb.left = s_left; sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p;
+            sb.nleft = 0; sb.left_d2 = 0; sb.k1 = k1; sb.nlam = nlam;
+            for (uint32_t rem = o.left; rem;) {
+                const int u = shb_top(rem);
+                rem ^= 1u << u;
+                const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
+                if (lane == 0) s_left[sb.nleft] = w;
+                sb.left_d2 |= ((o.left_d2 >> u) & 1u) << sb.nleft;
+                sb.nleft++;
+            }
+            __syncwarp();
+            int e, p, m;
+            t_term_shb(rows, sb, term, e, p, m);
+            __syncwarp();                                       // the lanes leave the elimination at different times
+            zw_add(z, e, p, m, sh_);
+            if (a.epm) {
+                int32_t* o3 = a.epm + ((size_t)idx * a.nterms + a.term_nat[g + lane]) * 3;
+                o3[0] = e; o3[1] = p; o3[2] = m & 7;
+            }
+            my_pairs++;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) z.a[j] += shfl_down_ll(z.a[j], d);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (z.a[j]) atomicAdd((unsigned long long*)&a.zw[(size_t)idx * 4 + j], (unsigned long long)z.a[j]);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) my_pairs += __shfl_down_sync(BG_FULL, my_pairs, d);
+    if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
+}
+
 // generic pairs: one warp per pair
 template <int NS>
 __global__ void __launch_bounds__(128) k_inner_products(const bg_state* a, const bg_state* b, size_t n_pairs, int32_t* epm) {
@@ -607,6 +700,10 @@ struct bg_ctx {
     uint64_t* d_terms = nullptr; size_t d_terms_cap = 0;             // natural order
     uint64_t* d_terms_sorted = nullptr; size_t d_terms_sorted_cap = 0;  // by popcount (pair kernels)
     int32_t* d_term_nat = nullptr; size_t d_term_nat_cap = 0;
+    // shared high-block plan (bg_shb_plan.h): relabelled, pattern-sorted terms for k_pairs_shb
+    ShbPlan shb_plan; int use_shb = 1;          // BG_SHB=0 disables
+    uint64_t* d_terms_shb = nullptr; size_t d_terms_shb_cap = 0;
+    int32_t* d_term_nat_shb = nullptr; size_t d_term_nat_shb_cap = 0;
     double* d_cdf = nullptr; int cdf_t = -1;
     // buffers
     SampleRec* d_recs = nullptr; size_t recs_cap = 0;
@@ -728,6 +825,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e5 = getenv("BG_GRAPH")) ctx->use_graph = atoi(e5) != 0;
     if (const char* e6 = getenv("BG_LAM_MAX")) ctx->lam_max = std::max(0, std::min(TPP_MAXC, atoi(e6)));
     if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
+    if (const char* e8 = getenv("BG_SHB")) ctx->use_shb = atoi(e8) != 0;
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
     *out = ctx;
@@ -738,7 +836,7 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
-    cudaFree(ctx->d_terms); cudaFree(ctx->d_terms_sorted); cudaFree(ctx->d_term_nat); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
+    cudaFree(ctx->d_terms); cudaFree(ctx->d_terms_shb); cudaFree(ctx->d_term_nat_shb); cudaFree(ctx->d_terms_sorted); cudaFree(ctx->d_term_nat); cudaFree(ctx->d_cdf); cudaFree(ctx->d_recs); cudaFree(ctx->d_zw); cudaFree(ctx->d_zw2);
     cudaFree(ctx->d_per); cudaFree(ctx->d_per2); cudaFree(ctx->d_P); cudaFree(ctx->d_counters); cudaFree(ctx->d_red); cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket);
     for (int sl = 0; sl < 2; sl++) {
         if (ctx->ev0s[sl]) cudaEventDestroy(ctx->ev0s[sl]);
@@ -898,6 +996,19 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
         CK(cudaMemcpyAsync(ctx->d_term_nat, nat.data(), chi * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));       // the host vectors go out of scope
     }
+    ctx->shb_plan = ShbPlan();
+    if (!exact && ctx->use_shb && !ctx->force_warp && t > 32 && t <= 32 + SHB_MAXH && chi >= 32 && chi <= 2048) {
+        ctx->shb_plan = shb_make_plan(t, k, ctx->L, ctx->terms_host);
+        if (ctx->shb_plan.ok) {
+            std::vector<uint64_t> tp(padded, 0);
+            std::copy(ctx->shb_plan.terms.begin(), ctx->shb_plan.terms.end(), tp.begin());
+            if (ensure(ctx, &ctx->d_terms_shb, &ctx->d_terms_shb_cap, padded)) return 1;
+            if (ensure(ctx, &ctx->d_term_nat_shb, &ctx->d_term_nat_shb_cap, chi)) return 1;
+            CK(cudaMemcpyAsync(ctx->d_terms_shb, tp.data(), padded * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_term_nat_shb, ctx->shb_plan.nat.data(), chi * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     if (ctx->cdf_t != t) {
         double cdf[BG_MAX_T + 1];
         dimension_cdf(t, cdf);
@@ -959,6 +1070,7 @@ static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
     CK(cudaMemsetAsync(CNT(ctx) + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
     a.force_warp = ctx->force_warp;
+    a.shb = (ctx->shb_plan.ok && src != SRC_TERMS) ? 1 : 0;     // SRC_TERMS = the exact-norm path (tri mode): generic kernels
     if (!a.P2) a.n_first = a.n_samples;
     a.n_warp_routed = CNT(ctx) + 4 * ctx->cur + 2;
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
@@ -1031,15 +1143,35 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         const long long tneed = (long long)((items + tw - 1) / tw);
         if (tb > tneed) tb = tneed;
         if (tb < 1) tb = 1;
-        // samples with <= TPP_MAXC parity checks, then (returns at once if there are none) the rest
         a.counter = cnt;
-        a.lam_max = std::max(0, std::min(ctx->lam_max, (int)(8 * wb) - a.t));
-        size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, a.lam_max, false) * wb
-                      + (size_t)tpp_work_rows(a.t, a.lam_max, false) * 32 * tw * wb;
-        if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
-        else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
+        const bool shb = ctx->shb_plan.ok && !a.tri && a.smem_terms > 0;
+        if (shb) {
+            // shared high-block reduction: relabelled pattern-sorted terms, 32-bit rows (samples with <= SHB_MAXLAM checks)
+            PairArgs b = a;
+            b.terms = ctx->d_terms_shb; b.term_nat = ctx->d_term_nat_shb;
+            b.shb.nh = ctx->shb_plan.nh; b.shb.nsw = ctx->shb_plan.nsw;
+            for (int i = 0; i < SHB_MAXH; i++) { b.shb.swp[i] = ctx->shb_plan.swp[i]; b.shb.swq[i] = ctx->shb_plan.swq[i]; }
+            const size_t smem = (size_t)b.smem_terms * 8 + (size_t)tw * SHB_WARP_WORDS * 4 + (size_t)32 * 32 * tw * 4;
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_pairs_shb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_shb, 32 * tw, smem));
+            if (per_sm < 1) return fail(ctx, "k_pairs_shb does not fit an SM (%zu bytes of shared memory)", smem);
+            const int blocks_shb = (int)std::min<long long>(tb, (long long)ctx->sm_count * per_sm);
+            k_pairs_shb<<<blocks_shb, 32 * tw, smem, ctx->stream>>>(b);
+            CK(cudaGetLastError());
+            ctx->stats.launches++;
+        } else {
+            // samples with <= TPP_MAXC parity checks
+            a.lam_max = std::max(0, std::min(ctx->lam_max, (int)(8 * wb) - a.t));
+            size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, a.lam_max, false) * wb
+                          + (size_t)tpp_work_rows(a.t, a.lam_max, false) * 32 * tw * wb;
+            if (a.t <= 32) { if (launch_tpp_w<uint32_t, false>(ctx, a, (int)tb, smem)) return 1; }
+            else { if (launch_tpp_w<uint64_t, false>(ctx, a, (int)tb, smem)) return 1; }
+        }
+        // the rest (returns at once if there is none)
         a.counter = cnt + 3;
-        smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, 0, true) * wb + (size_t)tpp_work_rows(a.t, 0, true) * 32 * tw * wb;
+        a.lam_max = 0;
+        const size_t smem = (size_t)a.smem_terms * 8 + (size_t)tw * tpp_amb_rows(a.t, 0, true) * wb + (size_t)tpp_work_rows(a.t, 0, true) * 32 * tw * wb;
         if (a.t <= 32) return launch_tpp_w<uint32_t, true>(ctx, a, (int)tb, smem);
         return launch_tpp_w<uint64_t, true>(ctx, a, (int)tb, smem);
     }

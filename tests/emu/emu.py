@@ -36,9 +36,9 @@ def compact_state(s, A):
 
 
 class Emu:
-    def __init__(self):
+    def __init__(self, libname="libbgemu.so"):
         subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
-        lib = C.CDLL(os.path.join(HERE, "libbgemu.so"))
+        lib = C.CDLL(os.path.join(HERE, libname))
         lib.emu_inner_product.argtypes = [_P(State), _P(State), _P(C.c_int32)]
         lib.emu_terms.argtypes = [_P(State), _P(Projector), C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_uint64),
                                   _P(C.c_int32), _P(C.c_int), _P(C.c_int), _P(C.c_longlong)]
@@ -49,6 +49,9 @@ class Emu:
         lib.emu_measure_pauli.restype = C.c_int
         lib.emu_random_state.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(State),
                                          _P(C.c_uint64)]
+        lib.emu_terms_shb.argtypes = [_P(State), _P(Projector), C.c_int, C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_int32),
+                                      _P(C.c_int), _P(C.c_int), _P(C.c_longlong), _P(C.c_int)]
+        lib.emu_terms_shb.restype = C.c_int
         lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
         self.lib = lib
 
@@ -70,6 +73,18 @@ class Emu:
                                    u64_array(terms), epm.ctypes.data_as(_P(C.c_int32)), C.byref(npf),
                                    C.byref(k), zw)
         return dict(alive=alive, epm=epm, npf=npf.value, k=k.value, zw=list(zw))
+
+    def terms_shb(self, theta, P, project, t, L):
+        """the chi loop through the shared high-block reduction (k_pairs_shb's code); epm in natural term order.
+        alive = -1: the decomposition has no plan; -2: theta has more parity checks than that kernel takes."""
+        n = 1 << len(L)
+        epm = np.zeros((n, 3), dtype=np.int32)
+        npf, k = C.c_int(), C.c_int()
+        zw = (C.c_longlong * 4)()
+        hist = (C.c_int * 16)()
+        alive = self.lib.emu_terms_shb(C.byref(theta), C.byref(P), int(project), t, len(L), u64_array(L),
+                                       epm.ctypes.data_as(_P(C.c_int32)), C.byref(npf), C.byref(k), zw, hist)
+        return dict(alive=alive, epm=epm, npf=npf.value, k=k.value, zw=list(zw), nleft_hist=list(hist))
 
     def work_counters(self, reset=True):
         out = (C.c_ulonglong * 6)()

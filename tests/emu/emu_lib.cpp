@@ -5,8 +5,10 @@
 #include "bg_device.cuh"
 #include "bg_warp_ops.cuh"
 #include "bg_tpp.cuh"
+#include "bg_shb.cuh"
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 namespace emu {
 thread_local Warp* g_warp = nullptr;
@@ -144,6 +146,79 @@ int emu_terms_tpp(const bg_state* theta, const bg_projector* P, int project, int
                   const uint64_t* terms, int32_t* epm, int* npf_out, int* k_out, long long* zw_out) {
     if (t <= 32) return terms_tpp<1>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
     return terms_tpp<2>(theta, P, project, exact, t, nterms, terms, epm, npf_out, k_out, zw_out);
+}
+
+// The chi loop through the shared high-block reduction (bg_shb.cuh), as k_pairs_shb runs it: plan on the host,
+// relabelling + shb_reduce under the warp emulator, then one lane per term.  Returns -1 when the decomposition
+// has no plan, -2 when theta has more checks than the kernel takes (the device routes those to the generic kernel).
+int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int t, int k, const uint64_t* Lrows,
+                  int32_t* epm, int* npf_out, int* k_out, long long* zw_out, int* nleft_hist) {
+    std::vector<uint64_t> L(Lrows, Lrows + k), terms((size_t)1 << k);
+    for (size_t i = 0; i < terms.size(); i++) {
+        uint64_t x = 0;
+        for (int j = 0; j < k; j++) if ((i >> (k - 1 - j)) & 1) x ^= L[j];
+        terms[i] = x & (t >= 64 ? ~0ull : ((1ull << t) - 1));
+    }
+    ShbPlan pl = shb_make_plan(t, k, L, terms);
+    if (!pl.ok) return -1;
+    int alive = 1, npf = 0, k1 = 0, toomany = 0;
+    Zw ztot; ztot.a[0] = ztot.a[1] = ztot.a[2] = ztot.a[3] = 0;
+    static uint32_t red[32], left[SHB_MAXHT];
+    static uint32_t work[32][40];
+    static uint64_t Jrows[64], Cwrows[64];
+    emu::run([&]() {
+        Native<2> st; Ambient<2> am;
+        native_load<2>(st, theta);
+        int n = 0; bool ok = true;
+        make_ambient<2>(st, am);
+        if (project) ok = project_ambient<2>(am, P, n);
+        const int lane = bg_lane();
+        if (lane == 0) { alive = ok; npf = n; k1 = am.k1; }
+        if (!ok) return;
+        if (popcw(am.Cpend) > SHB_MAXLAM) { if (lane == 0) toomany = 1; return; }
+        for (int s = 0; s < 2; s++) { Jrows[lane + 32 * s] = am.f.J[s]; Cwrows[lane + 32 * s] = am.Cw[s]; }
+        __syncwarp();
+        ShbPerm pm; pm.nh = pl.nh; pm.nsw = pl.nsw;
+        for (int i = 0; i < SHB_MAXH; i++) { pm.swp[i] = pl.swp[i]; pm.swq[i] = pl.swq[i]; }
+        ShbForm f;
+        const int nlam = shb_load(Jrows, Cwrows, am.Cpend, am.Cbeta, am.f.D1, am.f.D2, am.f.Q, t, pm, f);
+        const uint32_t lam_bits = ((1u << nlam) - 1u) << pm.nh;
+        Zw z; z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+        for (size_t g = 0; g < terms.size(); g += 32) {
+            const uint64_t term = pl.terms[g + lane];
+            const uint32_t pattern = __shfl_sync(BG_FULL, (uint32_t)(term >> 32), 0);
+            ShbOut o; uint32_t Lr, Rr;
+            shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
+            __syncwarp();
+            red[lane] = Lr;
+            ShbBatch sb;
+            sb.red = red; sb.left = left; sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p;
+            sb.nleft = 0; sb.left_d2 = 0; sb.k1 = am.k1; sb.nlam = nlam;
+            for (uint32_t rem = o.left; rem;) {
+                const int u = shb_top(rem);
+                rem ^= 1u << u;
+                const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
+                if (lane == 0) left[sb.nleft] = w;
+                sb.left_d2 |= ((o.left_d2 >> u) & 1u) << sb.nleft;
+                sb.nleft++;
+            }
+            if (lane == 0 && nleft_hist) nleft_hist[sb.nleft < 15 ? sb.nleft : 15]++;
+            __syncwarp();
+            Rows<uint32_t> rows; rows.base = work[lane]; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
+            int e, p, m;
+            t_term_shb(rows, sb, term, e, p, m);
+            __syncwarp();
+            zw_add(z, e, p, m, t / 2 + 1);
+            if (epm) { const int nat = pl.nat[g + lane]; epm[3 * nat] = e; epm[3 * nat + 1] = p; epm[3 * nat + 2] = m; }
+        }
+        for (int j = 0; j < 4; j++) {                      // lanes take turns (the emulator runs them round-robin)
+            for (int l = 0; l < 32; l++) { if (lane == l) ztot.a[j] += z.a[j]; __syncwarp(); }
+        }
+    });
+    *npf_out = npf; *k_out = k1;
+    if (zw_out) for (int j = 0; j < 4; j++) zw_out[j] = ztot.a[j];
+    if (toomany) return -2;
+    return alive;
 }
 
 void emu_set_lam_max(int n) { g_emu_lam_max = n; }

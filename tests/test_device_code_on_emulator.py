@@ -173,3 +173,41 @@ def test_projection_in_ambient_coordinates(emu, oracle):
         dead += not want["alive"]
         factors += want["alive"] and want["projfactor"] < 1
     assert dead > 3 and factors > 20                                 # all the branches are exercised
+
+
+@pytest.mark.parametrize("stream,t_expected,k,ns", [("hs_t40_k9_bit0.txt", 40, 9, 3), ("hs_t40_k9_bit2.txt", 40, 10, 2),
+                                                    ("phase_estimation_q0.txt", 33, 9, 3)])
+@pytest.mark.parametrize("variant", ["libbgemu.so", "libbgemu_reloc1.so"], ids=["reloc4", "reloc1_pivoted_leftovers"])
+def test_shared_high_block_vs_oracle(oracle, stream, t_expected, k, ns, variant):
+    """k_pairs_shb's code (bg_shb.cuh: relabelling, warp-level reduction of the variables >= 32, 32-bit threads)
+    against the oracle, pair by pair, on theta drawn by the device RNG's CPU restatement and projected.
+    The reloc1 build gives a thread ONE free slot for leftover high variables, so that the (otherwise rare)
+    path that pivots the remaining ones as parity checks runs in most batches."""
+    from emu.emu import Emu
+    emu = Emu(variant)
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t = cfg["t"]
+    assert t == t_expected
+    rs = np.random.RandomState(11)
+    L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+    terms = [oracle.Lbits(i, L) for i in range(1 << k)]
+    seen = 0
+    hist = np.zeros(16, dtype=int)
+    for P in (G, H):
+        for s in range(ns):
+            th = oracle.random_state_philox(t, 13, 0, s)
+            want = oracle.sample_from_theta(th, P, False, L)
+            got = emu.terms_shb(th, P, 1, t, L)
+            assert got["alive"] != -1, "no shared high-block plan for this L"
+            if got["alive"] == -2:
+                continue
+            assert got["alive"] == want["alive"]
+            if not want["alive"]:
+                continue
+            seen += 1
+            hist += np.array(got["nleft_hist"])
+            assert all(epm_equal(tuple(got["epm"][i]), tuple(want["epm"][i])) for i in range(len(terms)))
+            sh, a, r2 = t // 2 + 1, got["zw"], 2 ** -0.5
+            tot = complex(a[0] + (a[1] - a[3]) * r2, a[2] + (a[1] + a[3]) * r2) / 2 ** sh
+            assert abs(tot - want["total"]) <= 1e-12 * max(1.0, abs(want["total"]))
+    assert seen >= ns
