@@ -166,7 +166,9 @@ BG_HD void t_shb_copy_in(const Rows<uint32_t>& J, const ShbBatch& sb, uint32_t k
 
 // <phi|theta> for one |L> term of the batch.  A = the term's variables (relabelled): low word = the active low
 // variables, high word = the batch's high pattern.
-BG_HD void t_term_shb(const Rows<uint32_t>& J, const ShbBatch& sb, uint64_t A, int& eps, int& p, int& m) {
+// nlmax: the largest number of leftovers among the batches the lanes of this warp work on (warp-uniform; selects the
+// copy-in variant), sb.nleft: this thread's own.
+BG_HD void t_term_shb(const Rows<uint32_t>& J, const ShbBatch& sb, uint64_t A, int nlmax, int& eps, int& p, int& m) {
     const uint32_t Alo = (uint32_t)A;
     const int k2 = tpopc(A);
     TF<uint32_t> f;
@@ -183,7 +185,7 @@ BG_HD void t_term_shb(const Rows<uint32_t>& J, const ShbBatch& sb, uint64_t A, i
             f.D2 = (f.D2 & ~fb) | (((sb.left_d2 >> i) & 1u) ? fb : 0u);
         }
     }
-    switch (nrel) {
+    switch (nlmax < SHB_RELOC ? nlmax : SHB_RELOC) {                  // rel[i] = 0 beyond this thread's own leftovers
         case 0: t_shb_copy_in<0>(J, sb, Alo, rel); break;
         case 1: t_shb_copy_in<1>(J, sb, Alo, rel); break;
         case 2: t_shb_copy_in<2>(J, sb, Alo, rel); break;

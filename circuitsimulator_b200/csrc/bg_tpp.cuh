@@ -802,6 +802,9 @@ BG_HD void t_oddblock32(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D1, uint
 #if defined(__CUDA_ARCH__)
 #define T_WARP_ALL(x) __all_sync(__activemask(), (x))
 #define T_WARP_ANY(x) __any_sync(__activemask(), (x))
+#elif defined(BG_EMU_FORCE_ANY)       // CPU build that takes every "some other lane needs it" branch
+#define T_WARP_ALL(x) (false)
+#define T_WARP_ANY(x) (true)
 #else
 #define T_WARP_ALL(x) (x)
 #define T_WARP_ANY(x) (x)

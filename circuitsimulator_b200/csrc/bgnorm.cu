@@ -96,7 +96,7 @@ struct PairArgs {
     // work items: first n_samples * chunks_per_sample big items (terms [c*chunk, (c+1)*chunk) below tail_start),
     // then n_samples * tail_chunks small ones of 32 terms each covering [tail_start, nterms) — big items
     // first, small ones last, so that the last wave is short (the counter hands them out in this order)
-    int chunk, chunks_per_sample, tail_start, tail_chunks;
+    int chunk, chunks_per_sample, tail_start, tail_chunks, tail_size;
     unsigned long long* counter;
     long long* zw;          // [n_samples][4]
     long long* zw2;         // [n_samples][4]   (exact-norm mode: off-diagonal part)
@@ -122,7 +122,7 @@ __device__ __forceinline__ void item_range(const PairArgs& a, unsigned long long
         const unsigned long long j = item - nbig;
         idx = (int)(j / (unsigned)a.tail_chunks);
         const int c = (int)(j % (unsigned)a.tail_chunks);
-        i0 = a.tail_start + 32 * c; i1 = min(a.nterms, i0 + 32);
+        i0 = a.tail_start + a.tail_size * c; i1 = min(a.nterms, i0 + a.tail_size);
     }
 }
 
@@ -447,21 +447,31 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
 // per batch (shb_reduce), every thread then eliminates a form on <= 32 variables in 32-bit words.
 // dynamic smem: [staged terms][per warp: 32 reduced rows + SHB_MAXHT leftover rows][working rows: 32 x blockDim words]
 // ------------------------------------------------------------------------------------------
-#define SHB_WARP_WORDS (32 + SHB_MAXHT)
+// A warp works on SHB_G classes (patterns) of one sample at a time: 32 / SHB_G lanes per class, and the terms of a
+// class are sorted by popcount, so the lanes that run together have active sets of nearly equal size (the warp
+// waits for its largest term): round r takes the r-th slice of each of the SHB_G classes.
+#ifndef SHB_G
+#define SHB_G 2
+#endif
+#define SHB_CLASS_WORDS (32 + SHB_MAXHT)
+#define SHB_WARP_WORDS (SHB_G * SHB_CLASS_WORDS)
 __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
     const int lane = bg_lane(), warp = threadIdx.x >> 5;
     constexpr int nwarps = BG_TPP_WARPS;
+    constexpr int LPG = 32 / SHB_G;                             // lanes per class
     const int t = a.t;
     uint64_t* s_terms = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* s_red = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.smem_terms * 8) + warp * SHB_WARP_WORDS;
-    uint32_t* s_left = s_red + 32;
+    uint32_t* s_warp = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.smem_terms * 8) + warp * SHB_WARP_WORDS;
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)a.smem_terms * 8) + nwarps * SHB_WARP_WORDS + threadIdx.x;
     if (a.smem_terms > 0) tma_stage(s_terms, a.terms, (uint32_t)a.smem_terms * 8u, &s_mbar);
     const uint64_t* terms = a.smem_terms > 0 ? s_terms : a.terms;
     Rows<uint32_t> rows; rows.base = s_rows; rows.stride = BG_TPP_THREADS;
     rows.sbase = smem_u32(s_rows); rows.sstride = BG_TPP_THREADS * 4u;
+    const int h = lane / LPG;                                   // the class of the group this lane works on
+    uint32_t* my_red = s_warp + h * SHB_CLASS_WORDS;
+    uint32_t* my_left = my_red + 32;
 
     const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
     const int sh_ = t / 2 + 1;
@@ -482,34 +492,46 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
         const uint32_t lam_bits = ((1u << nlam) - 1u) << a.shb.nh;
         Zw z;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
-        for (int g = i0; g < i1; g += 32) {                     // every batch of 32 terms has one high pattern
-            const uint64_t term = terms[g + lane];
-            const uint32_t pattern = __shfl_sync(BG_FULL, (uint32_t)(term >> 32), 0);
-            ShbOut o; uint32_t Lr, Rr;
-            shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
-            __syncwarp();
-            s_red[lane] = Lr;
+        for (int g = i0; g < i1; g += 32 * SHB_G) {             // SHB_G classes of 32 terms; every class has one high pattern
             ShbBatch sb;
-            sb.red = s_red; sb.left = s_left; sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p;
-            sb.nleft = 0; sb.left_d2 = 0; sb.k1 = k1; sb.nlam = nlam;
-            for (uint32_t rem = o.left; rem;) {
-                const int u = shb_top(rem);
-                rem ^= 1u << u;
-                const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
-                if (lane == 0) s_left[sb.nleft] = w;
-                sb.left_d2 |= ((o.left_d2 >> u) & 1u) << sb.nleft;
-                sb.nleft++;
+            sb.red = my_red; sb.left = my_left; sb.k1 = k1; sb.nlam = nlam;
+            sb.D1 = sb.D2 = sb.Q = 0; sb.p = 0; sb.nleft = 0; sb.left_d2 = 0;
+            int nlmax = 0;
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < SHB_G; c++) {
+                const uint32_t pattern = (uint32_t)(terms[g + 32 * c] >> 32);
+                ShbOut o; uint32_t Lr, Rr;
+                shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
+                uint32_t* red = s_warp + c * SHB_CLASS_WORDS;
+                red[lane] = Lr;
+                int nleft = 0; uint32_t ld2 = 0;
+                for (uint32_t rem = o.left; rem;) {
+                    const int u = shb_top(rem);
+                    rem ^= 1u << u;
+                    const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
+                    if (lane == 0) red[32 + nleft] = w;
+                    ld2 |= ((o.left_d2 >> u) & 1u) << nleft;
+                    nleft++;
+                }
+                nlmax = max(nlmax, nleft);
+                if (h == c) { sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p; sb.nleft = nleft; sb.left_d2 = ld2; }
             }
             __syncwarp();
-            int e, p, m;
-            t_term_shb(rows, sb, term, e, p, m);
-            __syncwarp();                                       // the lanes leave the elimination at different times
-            zw_add(z, e, p, m, sh_);
-            if (a.epm) {
-                int32_t* o3 = a.epm + ((size_t)idx * a.nterms + a.term_nat[g + lane]) * 3;
-                o3[0] = e; o3[1] = p; o3[2] = m & 7;
+#pragma unroll 1
+            for (int rd = 0; rd < SHB_G; rd++) {
+                const int ti = g + 32 * h + LPG * rd + (lane & (LPG - 1));
+                const uint64_t term = terms[ti];
+                int e, p, m;
+                t_term_shb(rows, sb, term, nlmax, e, p, m);
+                __syncwarp();                                   // the lanes leave the elimination at different times
+                zw_add(z, e, p, m, sh_);
+                if (a.epm) {
+                    int32_t* o3 = a.epm + ((size_t)idx * a.nterms + a.term_nat[ti]) * 3;
+                    o3[0] = e; o3[1] = p; o3[2] = m & 7;
+                }
+                my_pairs++;
             }
-            my_pairs++;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -997,7 +1019,7 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
         CK(cudaStreamSynchronize(ctx->stream));       // the host vectors go out of scope
     }
     ctx->shb_plan = ShbPlan();
-    if (!exact && ctx->use_shb && !ctx->force_warp && t > 32 && t <= 32 + SHB_MAXH && chi >= 32 && chi <= 2048) {
+    if (!exact && ctx->use_shb && !ctx->force_warp && t > 32 && t <= 32 + SHB_MAXH && chi >= 32 * SHB_G && chi % (32 * SHB_G) == 0 && chi <= 2048) {
         ctx->shb_plan = shb_make_plan(t, k, ctx->L, ctx->terms_host);
         if (ctx->shb_plan.ok) {
             std::vector<uint64_t> tp(padded, 0);
@@ -1114,14 +1136,17 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     const int want_items = resident_warps * ctx->items_factor;
     // the last quarter of the (popcount-sorted, i.e. cheapest) terms goes out in 32-term items
     // (only when samples are scarce: with plenty of samples the big items balance by themselves)
-    const int tail_terms = (a.nterms >= 128 && a.n_samples < want_items) ? (((a.nterms / 4) + 31) & ~31) : 0;
+    const bool shb = ctx->shb_plan.ok && !a.tri && !ctx->force_warp && (((size_t)a.nterms + 1) & ~(size_t)1) <= 2048;
+    const int gran = shb ? 32 * SHB_G : 32;                    // items are whole groups of terms
+    const int tail_terms = (a.nterms >= 128 && a.n_samples < want_items) ? (((a.nterms / 4) + gran - 1) / gran * gran) : 0;
     a.tail_start = a.nterms - tail_terms;
-    a.tail_chunks = (tail_terms + 31) / 32;
+    a.tail_size = gran;
+    a.tail_chunks = (tail_terms + gran - 1) / gran;
     int cps = 1;
     if (a.n_samples < want_items) cps = (want_items + a.n_samples - 1) / a.n_samples;
     int chunk = (a.tail_start + cps - 1) / cps;
-    chunk = (chunk + 31) & ~31;                                // whole groups of 32 terms
-    if (chunk < 32) chunk = 32;
+    chunk = (chunk + gran - 1) / gran * gran;
+    if (chunk < gran) chunk = gran;
     cps = (a.tail_start + chunk - 1) / chunk;
     a.chunk = chunk; a.chunks_per_sample = cps;
     const size_t padded = ((size_t)a.nterms + 1) & ~(size_t)1;
@@ -1144,7 +1169,6 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
         if (tb > tneed) tb = tneed;
         if (tb < 1) tb = 1;
         a.counter = cnt;
-        const bool shb = ctx->shb_plan.ok && !a.tri && a.smem_terms > 0;
         if (shb) {
             // shared high-block reduction: relabelled pattern-sorted terms, 32-bit rows (samples with <= SHB_MAXLAM checks)
             PairArgs b = a;

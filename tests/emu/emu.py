@@ -52,6 +52,8 @@ class Emu:
         lib.emu_terms_shb.argtypes = [_P(State), _P(Projector), C.c_int, C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_int32),
                                       _P(C.c_int), _P(C.c_int), _P(C.c_longlong), _P(C.c_int)]
         lib.emu_terms_shb.restype = C.c_int
+        lib.emu_expsum_selftest.argtypes = [C.c_int, C.c_ulonglong, C.c_int]
+        lib.emu_expsum_selftest.restype = C.c_int
         lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
         self.lib = lib
 

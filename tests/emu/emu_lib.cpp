@@ -51,6 +51,9 @@ BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
 int* g_bg_trace = nullptr; int g_bg_trace_n = 0, g_bg_trace_cap = 0;
 using namespace bg;
 
+#ifndef EMU_SHB_G
+#define EMU_SHB_G 2
+#endif
 static int g_emu_lam_max = 4;   // checks carried as Lagrange variables (as k_pairs_tpp does; 0: every check pivoted per term)
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
 // ambient form is produced by the warp-level code under emulation, each term is then a plain call.
@@ -118,6 +121,68 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
     return alive;
 }
 
+// Brute-force self-test of the thread-level exponential sums (bg_tpp.cuh): random forms on n <= 14 variables
+// scattered over the word, sum_{x} e^{i pi q(x)/4} by enumeration against t_expsum_odd (free slots: none / a few /
+// all, which exercises the borrowed-variable steps and their hand-over to the rounds) and t_expsum (fold + dimers).
+// Returns the number of mismatches.
+template <typename W> static int expsum_selftest(uint64_t seed, int trials) {
+    const int bits = 8 * (int)sizeof(W);
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    int bad = 0;
+    for (int trial = 0; trial < trials; trial++) {
+        const int n = 1 + (int)(rnd() % 13);
+        W A = 0;
+        while (tpopc(A) < n) A |= (W)1 << (rnd() % bits);
+        const unsigned podd = (unsigned)(rnd() % 5), pj = 1 + (unsigned)(rnd() % 4);
+        W J[64], D1 = 0, D2 = (W)rnd() & A;
+        for (int a = 0; a < bits; a++) { J[a] = 0; if (((A >> a) & 1) && rnd() % 4 < podd) D1 |= (W)1 << a; }
+        for (int a = 0; a < bits; a++) for (int b = a + 1; b < bits; b++)
+            if (((A >> a) & 1) && ((A >> b) & 1) && rnd() % 5 < pj) { J[a] |= (W)1 << b; J[b] |= (W)1 << a; }
+        for (int a = 0; a < bits; a++) if ((D1 >> a) & 1) J[a] |= (W)1 << a;
+        const uint32_t Q = (uint32_t)(rnd() % 8);
+        int vars[64], nv = 0;
+        for (int a = 0; a < bits; a++) if ((A >> a) & 1) vars[nv++] = a;
+        long long z[4] = {0, 0, 0, 0};                       // coefficients of 1, w, w^2, w^3
+        for (uint32_t mk = 0; mk < (1u << nv); mk++) {
+            W x = 0;
+            for (int i = 0; i < nv; i++) if ((mk >> i) & 1) x |= (W)1 << vars[i];
+            int q = (int)Q;
+            for (int i = 0; i < nv; i++) {
+                const int a = vars[i];
+                if (!((x >> a) & 1)) continue;
+                q += 2 * (int)((D1 >> a) & 1) + 4 * (int)((D2 >> a) & 1);
+                q += 4 * tpopc((W)(J[a] & x & ~((((W)2) << a) - 1)));
+            }
+            q &= 7;
+            if (q < 4) z[q]++; else z[q - 4]--;
+        }
+        for (int variant = 0; variant < 4; variant++) {
+            W work[64];
+            for (int a = 0; a < bits; a++) work[a] = J[a] & A;
+            Rows<W> rows; rows.base = work; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
+            TF<W> f; f.A = A; f.D1 = D1; f.D2 = D2; f.Q = Q;
+            int e, p, m;
+            if (variant == 3) t_expsum<W>(rows, f, e, p, m);
+            else {
+                uint32_t fr = ~(uint32_t)A;
+                if (variant == 0) fr = 0;
+                if (variant == 1) { uint32_t k = 0; for (int i = 0; i < 2 && (fr & ~k); i++) k |= 1u << __builtin_ctz(fr & ~k); fr = k; }
+                t_expsum_odd(rows, f, e, p, m, fr);
+            }
+            // eps 2^(p/2) w^m as integer coefficients: p even -> 2^(p/2) w^m; p odd -> 2^((p-1)/2) (w^(m+1) + w^(m-1))
+            long long g[4] = {0, 0, 0, 0};
+            if (e) {
+                auto addw = [&](int mm, long long c) { mm &= 7; if (mm < 4) g[mm] += c; else g[mm - 4] -= c; };
+                if (p % 2 == 0) addw(m, 1ll << (p / 2));
+                else { addw(m + 1, 1ll << ((p - 1) / 2)); addw(m - 1, 1ll << ((p - 1) / 2)); }
+            }
+            if (g[0] != z[0] || g[1] != z[1] || g[2] != z[2] || g[3] != z[3]) bad++;
+        }
+    }
+    return bad;
+}
+
 extern "C" {
 
 // <b|a> through the generic path
@@ -163,7 +228,7 @@ int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int
     if (!pl.ok) return -1;
     int alive = 1, npf = 0, k1 = 0, toomany = 0;
     Zw ztot; ztot.a[0] = ztot.a[1] = ztot.a[2] = ztot.a[3] = 0;
-    static uint32_t red[32], left[SHB_MAXHT];
+    static uint32_t red[4 * 48];
     static uint32_t work[32][40];
     static uint64_t Jrows[64], Cwrows[64];
     emu::run([&]() {
@@ -184,32 +249,42 @@ int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int
         const int nlam = shb_load(Jrows, Cwrows, am.Cpend, am.Cbeta, am.f.D1, am.f.D2, am.f.Q, t, pm, f);
         const uint32_t lam_bits = ((1u << nlam) - 1u) << pm.nh;
         Zw z; z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
-        for (size_t g = 0; g < terms.size(); g += 32) {
-            const uint64_t term = pl.terms[g + lane];
-            const uint32_t pattern = __shfl_sync(BG_FULL, (uint32_t)(term >> 32), 0);
-            ShbOut o; uint32_t Lr, Rr;
-            shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
-            __syncwarp();
-            red[lane] = Lr;
+        const int LPG = 32 / EMU_SHB_G, hh = lane / LPG;      // as k_pairs_shb: EMU_SHB_G classes at a time, 32 / G lanes each
+        for (size_t g = 0; g < terms.size(); g += 32 * EMU_SHB_G) {
             ShbBatch sb;
-            sb.red = red; sb.left = left; sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p;
-            sb.nleft = 0; sb.left_d2 = 0; sb.k1 = am.k1; sb.nlam = nlam;
-            for (uint32_t rem = o.left; rem;) {
-                const int u = shb_top(rem);
-                rem ^= 1u << u;
-                const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
-                if (lane == 0) left[sb.nleft] = w;
-                sb.left_d2 |= ((o.left_d2 >> u) & 1u) << sb.nleft;
-                sb.nleft++;
+            sb.red = red + hh * 48; sb.left = red + hh * 48 + 32; sb.k1 = am.k1; sb.nlam = nlam;
+            sb.D1 = sb.D2 = sb.Q = 0; sb.p = 0; sb.nleft = 0; sb.left_d2 = 0;
+            int nlmax = 0;
+            __syncwarp();
+            for (int c = 0; c < EMU_SHB_G; c++) {
+                const uint32_t pattern = (uint32_t)(pl.terms[g + 32 * c] >> 32);
+                ShbOut o; uint32_t Lr, Rr;
+                shb_reduce(f, pattern | lam_bits, Lr, Rr, o);
+                red[c * 48 + lane] = Lr;
+                int nleft = 0; uint32_t ld2 = 0;
+                for (uint32_t rem = o.left; rem;) {
+                    const int u = shb_top(rem);
+                    rem ^= 1u << u;
+                    const uint32_t w = __shfl_sync(BG_FULL, Rr, u);
+                    if (lane == 0) red[c * 48 + 32 + nleft] = w;
+                    ld2 |= ((o.left_d2 >> u) & 1u) << nleft;
+                    nleft++;
+                }
+                if (lane == 0 && nleft_hist) nleft_hist[nleft < 15 ? nleft : 15]++;
+                nlmax = std::max(nlmax, nleft);
+                if (hh == c) { sb.D1 = o.D1; sb.D2 = o.D2; sb.Q = o.Q; sb.p = (int)o.p; sb.nleft = nleft; sb.left_d2 = ld2; }
             }
-            if (lane == 0 && nleft_hist) nleft_hist[sb.nleft < 15 ? sb.nleft : 15]++;
             __syncwarp();
-            Rows<uint32_t> rows; rows.base = work[lane]; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
-            int e, p, m;
-            t_term_shb(rows, sb, term, e, p, m);
-            __syncwarp();
-            zw_add(z, e, p, m, t / 2 + 1);
-            if (epm) { const int nat = pl.nat[g + lane]; epm[3 * nat] = e; epm[3 * nat + 1] = p; epm[3 * nat + 2] = m; }
+            for (int rd = 0; rd < EMU_SHB_G; rd++) {
+                const size_t ti = g + 32 * hh + LPG * rd + (lane & (LPG - 1));
+                const uint64_t term = pl.terms[ti];
+                Rows<uint32_t> rows; rows.base = work[lane]; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
+                int e, p, m;
+                t_term_shb(rows, sb, term, nlmax, e, p, m);
+                __syncwarp();
+                zw_add(z, e, p, m, t / 2 + 1);
+                if (epm) { const int nat = pl.nat[ti]; epm[3 * nat] = e; epm[3 * nat + 1] = p; epm[3 * nat + 2] = m; }
+            }
         }
         for (int j = 0; j < 4; j++) {                      // lanes take turns (the emulator runs them round-robin)
             for (int l = 0; l < 32; l++) { if (lane == l) ztot.a[j] += z.a[j]; __syncwarp(); }
@@ -219,6 +294,10 @@ int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int
     if (zw_out) for (int j = 0; j < 4; j++) zw_out[j] = ztot.a[j];
     if (toomany) return -2;
     return alive;
+}
+
+int emu_expsum_selftest(int wordbits, unsigned long long seed, int trials) {
+    return wordbits == 32 ? expsum_selftest<uint32_t>(seed, trials) : expsum_selftest<uint64_t>(seed, trials);
 }
 
 void emu_set_lam_max(int n) { g_emu_lam_max = n; }

@@ -211,3 +211,15 @@ def test_shared_high_block_vs_oracle(oracle, stream, t_expected, k, ns, variant)
             tot = complex(a[0] + (a[1] - a[3]) * r2, a[2] + (a[1] + a[3]) * r2) / 2 ** sh
             assert abs(tot - want["total"]) <= 1e-12 * max(1.0, abs(want["total"]))
     assert seen >= ns
+
+
+@pytest.mark.parametrize("variant", ["libbgemu.so", "libbgemu_any.so"])
+@pytest.mark.parametrize("wordbits", [32, 64])
+def test_exponential_sums_by_enumeration(variant, wordbits):
+    """The thread-level exponential sums of k_pairs_tpp / k_pairs_shb (odd-first with no / few / all free slots,
+    and the fold + dimer rounds) against sum_x e^{i pi q(x)/4} enumerated over all x, exact integer compare, on
+    random forms with <= 13 variables scattered over the word (zeros, all-even forms and out-of-slots hand-overs
+    included).  libbgemu_any.so takes every warp-vote branch the way a lane does when OTHER lanes ask for it."""
+    from emu.emu import Emu
+    emu = Emu(variant)
+    assert emu.lib.emu_expsum_selftest(wordbits, 7, 20000) == 0
