@@ -96,6 +96,7 @@ def load_library():
         "bg_sampled_norm2": [vp, _P(Projector), _P(Projector), u64, i32, u64, u64, dbl, _P(dbl)],
         "bg_sampled_prepare2": [vp, _P(Projector), _P(Projector), u64, i32, u64, u64],
         "bg_sampled_finish2": [vp, dbl, _P(dbl)],
+        "bg_sampled_per_sample": [vp, i32, u64, C.c_size_t, _P(dbl)],
         "bg_set_stream": [vp, vp],
         "bg_measure_int_peak": [vp, _P(dbl), _P(dbl)],
         "bg_decomposition_weights": [vp, i32, i32, _P(u64), _P(u64)],
@@ -119,7 +120,7 @@ def exported_symbols():
             "bg_sampled_norm", "bg_exact_norm", "bg_inner_products", "bg_sampled_norm_from_states",
             "bg_measure_pauli", "bg_random_states", "bg_decomposition_terms", "bg_get_stats",
             "bg_sampled_prepare", "bg_sampled_run", "bg_sampled_finish", "bg_sampled_norm2", "bg_sampled_prepare2",
-            "bg_sampled_finish2", "bg_set_stream", "bg_measure_int_peak", "bg_decomposition_weights"]
+            "bg_sampled_finish2", "bg_sampled_per_sample", "bg_set_stream", "bg_measure_int_peak", "bg_decomposition_weights"]
 
 
 def _states_arg(arr):
@@ -209,6 +210,12 @@ class Backend:
         return out[0], out[1]
 
     # -- parity / debug
+    def sampled_per_sample(self, projector, first, count):
+        """per-sample values of the last finished device-RNG job (this rank's local sample indices first .. first+count)"""
+        out = np.zeros(count, dtype=np.float64)
+        self._ck(self.lib.bg_sampled_per_sample(self.ctx, int(projector), first, count, out.ctypes.data_as(_P(C.c_double))))
+        return out
+
     def inner_products(self, a, b):
         a, pa = _states_arg(a)
         b, pb = _states_arg(b)

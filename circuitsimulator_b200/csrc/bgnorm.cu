@@ -751,6 +751,8 @@ struct bg_ctx {
     int nproj = 1;                  // projectors of the prepared job (2: numerator and denominator together)
     uint64_t samples = 0; int bins = 1; uint64_t seeds[2] = {0, 0};
     bool prepared = false;
+    bool per_valid = false;         // d_per holds the per-sample values of a finished job
+    bg_projector h_P[2];            // what d_P holds (a repeated prepare with the same content keeps the captured graph)
     bool phase_events = false;
     int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
     // the prepared job replayed as one CUDA graph (BG_GRAPH=0 disables)
@@ -777,6 +779,14 @@ static int fail(bg_ctx* ctx, const char* fmt, ...) {
     return 1;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// scratch device buffer of one call: freed on every return path
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, n * sizeof(T)); }
+    operator T*() const { return p; }
+};
 
 static cudaError_t rec_event(bg_ctx* ctx, cudaEvent_t ev) {
     return ctx->capturing ? cudaEventRecordWithFlags(ev, ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ev, ctx->stream);
@@ -878,6 +888,7 @@ extern "C" int bg_set_shard(bg_ctx* ctx, int rank, int world) {
     if (!ctx) return fail(nullptr, "bg_set_shard: null ctx");
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "bg_set_shard: bad rank %d of %d", rank, world);
     ctx->rank = rank; ctx->world = world;
+    ctx->prepared = false;
     drop_graph(ctx);
     return 0;
 }
@@ -971,6 +982,14 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
     if (!ctx) return fail(nullptr, "bg_set_decomposition: null ctx");
     if (t < 1 || t > BG_MAX_T) return fail(ctx, "bg_set_decomposition: t = %d outside 1..%d", t, BG_MAX_T);
     CK(cudaSetDevice(ctx->device));
+    if (ctx->t == t && ctx->exact == (exact ? 1 : 0) && !ctx->terms_host.empty()) {
+        // the same decomposition as the one in place (the back end sets it once per probability() call): keep the
+        // term tables, the plan, the prepared job and its captured graph
+        const uint64_t maskt = t >= 64 ? ~0ull : ((1ull << t) - 1);
+        bool same = exact ? true : (k == ctx->k && (k == 0 || L_rows != nullptr));
+        for (int j = 0; same && !exact && j < k; j++) same = (L_rows[j] & maskt) == ctx->L[j];
+        if (same) return 0;
+    }
     size_t chi;
     if (exact) {
         const int size = (t + 1) / 2;
@@ -1253,14 +1272,21 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     }
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
+    if (ctx->prepared && ctx->nproj == nproj && ctx->samples == samples && ctx->bins == bins) {
+        // the job that is already prepared (same projectors, sizes and seeds): nothing to upload, the graph stays
+        bool same = true;
+        for (int j = 0; same && j < nproj; j++)
+            same = ctx->seeds[j] == seeds[j] && memcmp(&ctx->h_P[j], Ps[j], sizeof(bg_projector)) == 0;
+        if (same) { ctx->stats.h2d_bytes = 0; return 0; }
+    }
     if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
     for (int j = 0; j < nproj; j++)
         CK(cudaMemcpyAsync(ctx->d_P + j, Ps[j], sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // the caller's projector may be a temporary
     ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
     ctx->nproj = nproj; ctx->samples = samples; ctx->bins = bins;
-    for (int j = 0; j < nproj; j++) ctx->seeds[j] = seeds[j];
-    ctx->prepared = true;
+    for (int j = 0; j < nproj; j++) { ctx->seeds[j] = seeds[j]; ctx->h_P[j] = *Ps[j]; }
+    ctx->prepared = true; ctx->per_valid = false;
     drop_graph(ctx);
     return 0;
 }
@@ -1452,6 +1478,7 @@ static int sampled_finish_n(bg_ctx* ctx, double* out) {
         ctx->stats.launches = fused2(ctx) ? 4 : (uint64_t)ctx->nproj * ctx->bins * 4;
     ctx->stats.pair_launches = fused2(ctx) ? 1 : (uint64_t)ctx->nproj * ctx->bins;
     ctx->phase_events = true;
+    ctx->per_valid = true;
     const int rc = collect_stats(ctx, ctx->nproj, true);
     for (int pj = 0; pj < ctx->nproj && !rc; pj++) {
         std::vector<double> v(ctx->bins);
@@ -1503,6 +1530,7 @@ extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samp
     ctx->stats.kernel_ms = total_ms; ctx->stats.pairs = total_pairs; ctx->stats.launches = launches;
     ctx->stats.prepare_ms = prep_ms; ctx->stats.pairs_ms = pair_ms;
     ctx->stats.d2h_bytes = bins * sizeof(double);
+    ctx->per_valid = true;
     *out = median_like_reference(v);
     return 0;
 }
@@ -1518,19 +1546,28 @@ extern "C" int bg_sampled_norm2(bg_ctx* ctx, const bg_projector* G, const bg_pro
         if (bg_sampled_norm(ctx, G, samples, bins, seed_g, norm, &out[0])) return 1;
         return bg_sampled_norm(ctx, H, samples, bins, seed_h, norm, &out[1]);
     }
-    if (bg_sampled_prepare2(ctx, G, H, samples, bins, seed_g, seed_h)) return 1;
-    ctx->stats.launches = 0;
-    ctx->slot = (int)(ctx->run_seq & 1u);
-    int rc = enqueue_job(ctx);
-    if (!rc) rc = enqueue_collect(ctx);
-    ctx->slot = 0;
-    if (rc) return 1;
-    ctx->run_seq++;
-    const bool ug = ctx->use_graph;
-    ctx->use_graph = false;                  // launches were counted one by one
-    rc = sampled_finish_n(ctx, out);
-    ctx->use_graph = ug;
-    return rc;
+    if (bg_sampled_prepare2(ctx, G, H, samples, bins, seed_g, seed_h)) return 1;      // no-op when this job is already prepared
+    if (bg_sampled_run(ctx)) return 1;                                               // replays the captured graph
+    return sampled_finish_n(ctx, out);
+}
+
+extern "C" int bg_sampled_per_sample(bg_ctx* ctx, int projector, uint64_t first, size_t count, double* out) {
+    if (!ctx) return fail(nullptr, "bg_sampled_per_sample: null ctx");
+    if (!ctx->prepared || !ctx->per_valid || ctx->run_seq != ctx->fin_seq)
+        return fail(ctx, "bg_sampled_per_sample: no finished sampled job");
+    if (projector < 0 || projector >= ctx->nproj) return fail(ctx, "bg_sampled_per_sample: projector %d of %d", projector, ctx->nproj);
+    if (count == 0) return 0;
+    if (!out) return fail(ctx, "bg_sampled_per_sample: null out");
+    const uint64_t mine = shard_count(ctx->samples, ctx->rank, ctx->world);
+    if (first + count > mine) return fail(ctx, "bg_sampled_per_sample: samples %llu..%llu of %llu on this rank",
+                                          (unsigned long long)first, (unsigned long long)(first + count), (unsigned long long)mine);
+    CK(cudaSetDevice(ctx->device));
+    // a fused two-projector job keeps both segments; otherwise d_per holds the projector that ran last
+    if (!fused2(ctx) && projector != ctx->nproj - 1)
+        return fail(ctx, "bg_sampled_per_sample: only the last projector's values are kept for this job (bins > 1 or BG_FUSE2=0)");
+    const size_t off = fused2(ctx) ? (size_t)projector * (size_t)mine : 0;
+    CK(cudaMemcpy(out, ctx->d_per + off + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // ---- exact norm ---------------------------------------------------------------------------
@@ -1548,6 +1585,7 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
     const uint64_t mine = shard_count(chi, ctx->rank, ctx->world);
     const int n = (int)mine;
     if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
+    ctx->prepared = false;                       // d_P no longer holds the prepared job's projectors
     CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes = sizeof(bg_projector);
     ctx->stats.launches = 0;
@@ -1604,10 +1642,8 @@ extern "C" int bg_inner_products(bg_ctx* ctx, size_t n_pairs, const bg_state* a,
     if (check_states(ctx, a, n_pairs, &ta) || check_states(ctx, b, n_pairs, &tb)) return 1;
     for (size_t i = 0; i < n_pairs; i++)
         if (a[i].n != b[i].n) return fail(ctx, "pair %zu: states of different size (%d vs %d)", i, a[i].n, b[i].n);
-    bg_state *da = nullptr, *db = nullptr; int32_t* de = nullptr;
-    CK(cudaMalloc((void**)&da, n_pairs * sizeof(bg_state)));
-    CK(cudaMalloc((void**)&db, n_pairs * sizeof(bg_state)));
-    CK(cudaMalloc((void**)&de, n_pairs * 3 * sizeof(int32_t)));
+    DevBuf<bg_state> da, db; DevBuf<int32_t> de;
+    CK(da.alloc(n_pairs)); CK(db.alloc(n_pairs)); CK(de.alloc(n_pairs * 3));
     CK(cudaMemcpyAsync(da, a, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(db, b, n_pairs * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)std::min<size_t>((n_pairs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (size_t)ctx->sm_count * 16);
@@ -1621,7 +1657,6 @@ extern "C" int bg_inner_products(bg_ctx* ctx, size_t n_pairs, const bg_state* a,
     float ms = 0; cudaEventElapsedTime(&ms, EV0(ctx), EV1(ctx));
     ctx->stats.kernel_ms = ms; ctx->stats.pairs = n_pairs; ctx->stats.launches = 1;
     ctx->stats.h2d_bytes = 2 * n_pairs * sizeof(bg_state); ctx->stats.d2h_bytes = n_pairs * 3 * sizeof(int32_t);
-    cudaFree(da); cudaFree(db); cudaFree(de);
     return 0;
 }
 
@@ -1640,12 +1675,13 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     const int n = (int)n_states;
     const size_t chi = ctx->terms_host.size();
     if (ensure_sample_buffers(ctx, n_states)) return 1;
-    bg_state* dth = nullptr; int32_t* depm = nullptr;
-    CK(cudaMalloc((void**)&dth, n_states * sizeof(bg_state)));
+    DevBuf<bg_state> dth; DevBuf<int32_t> depm;
+    CK(dth.alloc(n_states));
     CK(cudaMemcpyAsync(dth, thetas, n_states * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prepared = false;                       // d_P / the sample buffers no longer belong to the prepared job
     if (project) CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     if (epm) {
-        CK(cudaMalloc((void**)&depm, n_states * chi * 3 * sizeof(int32_t)));
+        CK(depm.alloc(n_states * chi * 3));
         CK(cudaMemsetAsync(depm, 0, n_states * chi * 3 * sizeof(int32_t), ctx->stream));
     }
     ctx->stats.launches = 0;
@@ -1673,7 +1709,6 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     ctx->stats.h2d_bytes = n_states * sizeof(bg_state);
     ctx->stats.d2h_bytes = sizeof(double) + (per_sample ? n_states * sizeof(double) : 0) + (epm ? n_states * chi * 12 : 0);
     if (mean) *mean = s / (double)n_states;
-    cudaFree(dth); if (depm) cudaFree(depm);
     return 0;
 }
 
@@ -1707,10 +1742,9 @@ extern "C" int bg_measure_pauli(bg_ctx* ctx, size_t n_states, bg_state* states, 
     int tt;
     if (check_states(ctx, states, n_states, &tt)) return 1;
     CK(cudaSetDevice(ctx->device));
-    bg_state* ds = nullptr; uint64_t *dA = nullptr, *dz = nullptr, *dx = nullptr; int32_t *dm = nullptr, *dc = nullptr;
-    CK(cudaMalloc((void**)&ds, n_states * sizeof(bg_state)));
-    CK(cudaMalloc((void**)&dA, n_states * 8)); CK(cudaMalloc((void**)&dz, n_states * 8)); CK(cudaMalloc((void**)&dx, n_states * 8));
-    CK(cudaMalloc((void**)&dm, n_states * 4)); CK(cudaMalloc((void**)&dc, n_states * 4));
+    DevBuf<bg_state> ds; DevBuf<uint64_t> dA, dz, dx; DevBuf<int32_t> dm, dc;
+    CK(ds.alloc(n_states)); CK(dA.alloc(n_states)); CK(dz.alloc(n_states)); CK(dx.alloc(n_states));
+    CK(dm.alloc(n_states)); CK(dc.alloc(n_states));
     CK(cudaMemcpyAsync(ds, states, n_states * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dz, zeta, n_states * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dx, xi, n_states * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1728,7 +1762,6 @@ extern "C" int bg_measure_pauli(bg_ctx* ctx, size_t n_states, bg_state* states, 
         compact_state(&states[i], A[i]);
         if (result) result[i] = code[i] == 0 ? 0.0 : (code[i] == 1 ? 1.0 : pow(2, -0.5));
     }
-    cudaFree(ds); cudaFree(dA); cudaFree(dz); cudaFree(dx); cudaFree(dm); cudaFree(dc);
     return 0;
 }
 
@@ -1738,9 +1771,8 @@ static int dump_states(bg_ctx* ctx, int src, int t, uint64_t seed, int bin, uint
     if (!out) return fail(ctx, "null output buffer");
     CK(cudaSetDevice(ctx->device));
     if (ensure_sample_buffers(ctx, count)) return 1;
-    bg_state* ds = nullptr; uint64_t* dA = nullptr;
-    CK(cudaMalloc((void**)&ds, count * sizeof(bg_state)));
-    CK(cudaMalloc((void**)&dA, count * 8));
+    DevBuf<bg_state> ds; DevBuf<uint64_t> dA;
+    CK(ds.alloc(count)); CK(dA.alloc(count));
     if (ctx->cdf_t != t && src == SRC_RNG) {
         double cdf[BG_MAX_T + 1];
         dimension_cdf(t, cdf);
@@ -1759,7 +1791,6 @@ static int dump_states(bg_ctx* ctx, int src, int t, uint64_t seed, int bin, uint
     CK(cudaMemcpyAsync(A.data(), dA, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < count; i++) compact_state(&out[i], A[i]);
-    cudaFree(ds); cudaFree(dA);
     return 0;
 }
 

@@ -193,6 +193,14 @@ int  bg_sampled_prepare2(bg_ctx* ctx, const bg_projector* G, const bg_projector*
                          uint64_t seed_g, uint64_t seed_h);
 int  bg_sampled_finish2(bg_ctx* ctx, double norm, double out[2]);
 
+/* Per-sample values of the most recent FINISHED device-RNG job (bg_sampled_norm, bg_sampled_norm2, or prepare /
+ * run / finish): out[i] = 2^t |projfactor * sum_j <theta_l|phi_j>|^2 (libcirc/innerprod.c:142) for this rank's
+ * local sample index first + i, i < count — global sample l = rank + (first + i) * world (bg_set_shard).
+ * projector: 0, or 1 for H' of a two-projector job.  With bins > 1 only the last bin is kept.  This is the
+ * read-back the parity tests use to spot-check a full-size run against the oracle on the same Philox theta
+ * (BG_DUMP). */
+int  bg_sampled_per_sample(bg_ctx* ctx, int projector, uint64_t first, size_t count, double* out);
+
 /* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
  * instead of the context's own, so that the caller's events bracket the kernels. */
 int  bg_set_stream(bg_ctx* ctx, void* cuda_stream);

@@ -544,3 +544,110 @@ def test_backend_fidelity_option_matches_compiled_reference():
         assert "%.17e" % num == c["numerator"] and "%.17e" % den == c["denominator"], (c["t"], c["k"], lines[-2:])
         delta = [float(re.search(r"delta = 1 - <H\^t\|L>: ([-0-9.eE]+)", ln).group(1)) for ln in lines if "delta" in ln]
         assert delta and delta[-1] == c["delta_printed"]
+
+
+# ----------------------------------------------------------------------------- parity at the headline sizes
+def _bench_L(k, t):
+    rs = np.random.RandomState(20240)                       # bench.py: fixed_L
+    return [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+
+
+def test_full_size_run_spot_checked_against_oracle(be, oracle):
+    """BASELINE config 4 as bench.py runs it (t=40, chi=512, L=2^16, both projectors in one fused job, device
+    RNG): the per-sample values of the FULL run are read back (bg_sampled_per_sample) and 64 random sample
+    indices per projector are re-computed by the oracle from the same Philox theta — value-level parity at
+    the headline size, through the shared high-block kernel."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t40_k9_bit0.txt"))
+    t = cfg["t"]
+    L = _bench_L(9, t)
+    be.set_decomposition(t, False, L)
+    samples = 65536
+    num, den = be.sampled_norm2(to_bg(G), to_bg(H), samples, 1, 1234, 5678, 1.0)
+    rs = np.random.RandomState(5)
+    for pj, (P, seed) in enumerate(((G, 1234), (H, 5678))):
+        per = be.sampled_per_sample(pj, 0, samples)
+        assert abs(per.sum() / samples - (num, den)[pj]) <= 1e-12 * abs((num, den)[pj])
+        for l in rs.randint(0, samples, 64):
+            th = oracle.random_state_philox(t, seed, 0, int(l))
+            want = oracle.sample_from_theta(th, P, False, L, want_epm=False)["value"]
+            assert abs(per[l] - want) <= RTOL * max(abs(want), 1e-300), (pj, int(l), per[l], want)
+
+
+@pytest.mark.parametrize("t,k,nsamples,stream", [(40, 9, 200, "hs_t40_k9_bit0.txt"), (60, 8, 400, None)])
+def test_hundred_thousand_pairs_vs_oracle(be, oracle, t, k, nsamples, stream):
+    """>= 10^5 inner products per configuration, amplitude by amplitude (eps, p, m mod 8), against the oracle on
+    the same device-drawn, projected thetas: t=40 / chi=512 (shared high-block kernel) and t=60 / chi=256
+    (generic 64-bit kernel)."""
+    if stream:
+        cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+        P, OP = to_bg(G), G
+    else:
+        P, OP = _random_projector(np.random.RandomState(60), t, 30)
+    L = _bench_L(k, t)
+    be.set_decomposition(t, False, L)
+    chi = 1 << k
+    thetas = be.random_states(t, 77, 0, 0, nsamples)
+    got = be.sampled_norm_from_states(P, thetas, project=True, want_epm=True, chi=chi)
+    pairs = bad = 0
+    for l in range(nsamples):
+        want = oracle.sample_from_theta(state_from_numpy(thetas[l]), OP, False, L)
+        if want["alive"]:
+            pairs += chi
+            bad += sum(not epm_equal(tuple(int(v) for v in got["epm"][l, i]), tuple(int(v) for v in want["epm"][i]))
+                       for i in range(chi))
+        assert abs(got["per_sample"][l] - want["value"]) <= RTOL * max(abs(want["value"]), 1e-300)
+    assert bad == 0
+    assert pairs >= 100000
+
+
+@pytest.mark.parametrize("stream", ["hs_t40_k9_bit0.txt", "hs_t16_bit6.txt"])
+def test_projection_of_two_thousand_thetas_vs_oracle(be, oracle, stream):
+    """The projection step (measurePauli per generator: alive, number of 2^-1/2 factors, dimension k1) for 2000
+    device-drawn thetas per real projector: the per-sample value against a small decomposition carries all three
+    (annihilated -> 0; npf and k1 enter the power of two)."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t = cfg["t"]
+    L = _bench_L(3, t)
+    be.set_decomposition(t, False, L)
+    thetas = be.random_states(t, 99, 0, 0, 2000)
+    for P in (G, H):
+        got = be.sampled_norm_from_states(to_bg(P), thetas, project=True)
+        wants = [oracle.sample_from_theta(state_from_numpy(th), P, False, L, want_epm=False) for th in thetas]
+        # the device sums exactly (integers); the oracle follows the reference's sequential cos / sin sum, which
+        # leaves ~1e-16 of the largest term where the exact sum is 0 — hence a floor on the tolerance
+        floor = RTOL * float(np.mean([abs(w["value"]) for w in wants]))
+        for l, want in enumerate(wants):
+            if not want["alive"]:
+                assert got["per_sample"][l] == 0.0
+            assert abs(got["per_sample"][l] - want["value"]) <= max(RTOL * abs(want["value"]), floor)
+
+
+def test_statistical_gate_htstack(be):
+    """End-to-end estimator check: circuits/HTstack.circ with 4 T gates, P(0) = 0.97855339
+    (HTstack.circ:10).  Mean over 64 seeds of the sampled ratio numerator / denominator, L = 1024 each, must sit
+    within 3 standard errors of the exact value — a sign or normalisation error in the estimator fails this."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "htstack_t4.txt"))
+    be.set_decomposition(cfg["t"], True)
+    Gb, Hb = to_bg(G), to_bg(H)
+    ratios = []
+    for seed in range(64):
+        num, den = be.sampled_norm2(Gb, Hb, 1024, 1, 1000 + seed, 5000 + seed, 1.0)
+        ratios.append(num / den)
+    ratios = np.array(ratios)
+    se = ratios.std(ddof=1) / np.sqrt(len(ratios))
+    assert se < 0.01
+    assert abs(ratios.mean() - 0.97855339) <= 3 * se + 1e-3, (ratios.mean(), se)   # 1e-3: bias of a ratio estimator ~ var/L
+
+
+def test_statistical_gate_sampled_vs_exact_norm_t16(be, oracle):
+    """Config 3 (hidden shift, t=16, exact decomposition chi=256): the sampled estimate of ||Pi|H^t>||^2 over
+    2^14 samples x 8 seeds against the exact-norm path on the same projector, within 3 standard errors."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
+    be.set_decomposition(cfg["t"], True)
+    for P in (G, H):
+        Pb = to_bg(P)
+        exact = be.exact_norm(Pb, 1.0)
+        est = np.array([be.sampled_norm(Pb, 16384, 1, 300 + s, 1.0) for s in range(8)])
+        se = est.std(ddof=1) / np.sqrt(len(est))
+        assert abs(est.mean() - exact) <= 3 * se, (est.mean(), exact, se)
+        assert se < 0.05 * exact
