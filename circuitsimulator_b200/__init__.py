@@ -75,6 +75,7 @@ def load_library():
     vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
     sig = {
         "bg_init": [_P(vp), i32],
+        "bg_device_count": [_P(i32)],
         "bg_set_shard": [vp, i32, i32],
         "bg_set_allreduce": [vp, i32],
         "bg_nccl_unique_id": [_P(C.c_uint8)],
@@ -115,7 +116,7 @@ def load_library():
 
 def exported_symbols():
     """Every entry point include/bgnorm.h declares (used by the CPU-side ABI test)."""
-    return ["bg_init", "bg_shutdown", "bg_last_error", "bg_set_shard", "bg_set_allreduce", "bg_nccl_unique_id", "bg_nccl_join",
+    return ["bg_init", "bg_device_count", "bg_shutdown", "bg_last_error", "bg_set_shard", "bg_set_allreduce", "bg_nccl_unique_id", "bg_nccl_join",
             "bg_set_decomposition", "bg_set_decomposition_bitmatrix", "bg_projector_from_bitmatrix",
             "bg_sampled_norm", "bg_exact_norm", "bg_inner_products", "bg_sampled_norm_from_states",
             "bg_measure_pauli", "bg_random_states", "bg_decomposition_terms", "bg_get_stats",

@@ -65,7 +65,7 @@ static inline ShbPlan shb_make_plan(int t, int k, const std::vector<uint64_t>& L
     std::vector<int> best;
     {
         std::vector<int> idx(std::max(r, 1));
-        long long budget = 4000000;
+        long long budget = 400000;                       // ~0.1 s at worst; a random L is found within a few hundred tries
         auto count_inside = [&](const ShbBasis& B, std::vector<int>& inside) {
             inside.clear();
             for (int c = 0; c < t; c++) if (B.reduce(col[c]) == 0) inside.push_back(c);
@@ -82,7 +82,7 @@ static inline ShbPlan shb_make_plan(int t, int k, const std::vector<uint64_t>& L
                 ShbBasis B;
                 for (int i = 0; i < r; i++) B.add(col[idx[i]]);
                 count_inside(B, inside);
-                if (inside.size() > best.size()) { best = inside; if ((int)best.size() >= nh + 2) break; }
+                if (inside.size() > best.size()) { best = inside; if ((int)best.size() >= nh) break; }     // the first hit will do
                 int i = r - 1;
                 while (i >= 0 && idx[i] == t - r + i) i--;
                 if (i < 0) break;

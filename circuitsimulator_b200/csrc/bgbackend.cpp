@@ -28,6 +28,9 @@
 
 #include <errno.h>
 #include <fcntl.h>
+#include <signal.h>
+#include <sys/stat.h>
+#include <sys/time.h>
 #include <sys/socket.h>
 #include <sys/un.h>
 
@@ -184,6 +187,13 @@ public:
     // returns "" on success
     std::string start() {
         if (started_) return "";
+        int ndev = 0;
+        if (bg_device_count(&ndev)) return std::string("bg_device_count: ") + bg_last_error(nullptr);
+        if (device0_ < 0 || device0_ + gpus_ > ndev) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "BG_GPUS=%d from device %d, but %d CUDA device(s) are visible", gpus_, device0_, ndev);
+            return buf;
+        }
         if (gpus_ > 1 && bg_nccl_unique_id(nccl_id_)) return std::string("bg_nccl_unique_id: ") + bg_last_error(nullptr);
         ready_ = 0;
         for (int r = 0; r < gpus_; r++) th_.emplace_back(&Engine::worker, this, r);
@@ -210,16 +220,35 @@ public:
     int gpus() const { return gpus_; }
 
 private:
+    // All ranks report whether they are fine and learn whether EVERY rank is: no rank enters a collective
+    // (ncclCommInitRank, the all-reduce of a job) that a failed peer would never join.
+    bool agree(bool ok) {
+        std::unique_lock<std::mutex> lk(mu_);
+        const unsigned long long round = agree_round_;
+        if (!ok) agree_bad_ = true;
+        if (++agree_count_ == gpus_) {
+            agree_result_ = !agree_bad_;
+            agree_count_ = 0; agree_bad_ = false; agree_round_++;
+            cv_agree_.notify_all();
+        } else {
+            cv_agree_.wait(lk, [&] { return agree_round_ != round; });
+        }
+        return agree_result_;
+    }
+
     void worker(int rank) {
         bg_ctx* ctx = nullptr;
         std::string err;
+        // phase 1: the context; phase 2 (only if every rank has one): the NCCL communicator
         if (bg_init(&ctx, device0_ + rank)) err = std::string("bg_init: ") + bg_last_error(nullptr);
         else if (bg_set_shard(ctx, rank, gpus_)) err = std::string("bg_set_shard: ") + bg_last_error(ctx);
-        else if (gpus_ > 1 && bg_nccl_join(ctx, nccl_id_)) err = std::string("bg_nccl_join: ") + bg_last_error(ctx);
+        const bool all_up = agree(err.empty());
+        if (all_up && gpus_ > 1 && bg_nccl_join(ctx, nccl_id_)) err = std::string("bg_nccl_join: ") + bg_last_error(ctx);
+        if (!all_up && err.empty()) err = "another GPU of the job failed to initialise";
         unsigned long long seen = 0;
         {
             std::unique_lock<std::mutex> lk(mu_);
-            if (!err.empty() && init_error_.empty()) init_error_ = err;
+            if (!err.empty() && (init_error_.empty() || init_error_[0] == 'a')) init_error_ = err;
             ready_++;
             cv_done_.notify_all();
         }
@@ -234,28 +263,37 @@ private:
             }
             std::string jerr = err;
             double num = 0, den = 0;
-            if (jerr.empty() && job->kind == Job::WEIGHTS) {       // decompose()'s fidelity loop: one GPU is plenty
-                if (rank == 0 && bg_decomposition_weights(ctx, job->c.t, (int)job->L.size(), job->L.data(), job->hist))
+            if (job->kind == Job::WEIGHTS) {       // decompose()'s fidelity loop: one GPU is plenty, no collective
+                if (jerr.empty() && rank == 0 && bg_decomposition_weights(ctx, job->c.t, (int)job->L.size(), job->L.data(), job->hist))
                     jerr = bg_last_error(ctx);
-            } else if (jerr.empty()) {
+            } else {
                 const Config& c = job->c;
-                int rc = bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data());
-                if (!rc) {
+                // everything that can fail on one rank alone (validation, allocation, uploads) comes first ...
+                int rc = jerr.empty() ? bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data()) : 1;
+                const bool split = c.noapprox == 0 && c.bins >= 1 && c.bins <= 4 && job->G.nstabs > 0 && job->H.nstabs > 0 &&
+                                   job->G.nqubits > 0 && job->H.nqubits > 0;
+                if (!rc && split)
+                    rc = bg_sampled_prepare2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
+                                             splitmix64(job->seed + 1));
+                if (rc && jerr.empty()) jerr = bg_last_error(ctx);
+                // ... then the ranks agree, and only then run what contains the all-reduce
+                if (agree(jerr.empty())) {
                     if (c.noapprox == 0) {            // multiSampledProjector x2 (probability.c:197-198)
                         double out[2] = {0, 0};
-                        rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
-                                              splitmix64(job->seed + 1), job->norm, out);
+                        if (split) { rc = bg_sampled_run(ctx); if (!rc) rc = bg_sampled_finish2(ctx, job->norm, out); }
+                        else rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
+                                                   splitmix64(job->seed + 1), job->norm, out);
                         num = out[0]; den = out[1];
                     } else {                          // exactProjector x2 (probability.c:200-201)
                         rc = bg_exact_norm(ctx, &job->G, job->norm, &num);
                         if (!rc) rc = bg_exact_norm(ctx, &job->H, job->norm, &den);
                     }
-                }
-                if (rc) jerr = bg_last_error(ctx);
+                    if (rc) jerr = bg_last_error(ctx);
+                } else if (jerr.empty()) jerr = "another GPU of the job reported an error";
             }
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                if (!jerr.empty() && job->error.empty()) job->error = jerr;
+                if (!jerr.empty() && (job->error.empty() || job->error[0] == 'a')) job->error = jerr;
                 if (rank == 0) { job->numerator = num; job->denominator = den; }
                 done_++;
                 cv_done_.notify_all();
@@ -268,7 +306,8 @@ private:
     uint8_t nccl_id_[128];
     std::vector<std::thread> th_;
     std::mutex mu_;
-    std::condition_variable cv_job_, cv_done_;
+    std::condition_variable cv_job_, cv_done_, cv_agree_;
+    int agree_count_ = 0; bool agree_bad_ = false, agree_result_ = true; unsigned long long agree_round_ = 0;
     Job* job_ = nullptr;
     unsigned long long generation_ = 0;
     int done_ = 0, ready_ = 0;
@@ -412,13 +451,18 @@ static int serve(const char* path, int gpus, int device0, bool chatter) {
     Engine engine(gpus, device0);
     std::string err = engine.start();
     if (!err.empty()) { fprintf(stderr, "bgbackend --serve: %s\n", err.c_str()); return 1; }
+    signal(SIGPIPE, SIG_IGN);                      // a client that goes away before reading its answer must not kill the server
     int srv = socket(AF_UNIX, SOCK_STREAM, 0);
     if (srv < 0) { perror("socket"); return 1; }
     sockaddr_un addr; memset(&addr, 0, sizeof addr);
     addr.sun_family = AF_UNIX;
-    strncpy(addr.sun_path, path, sizeof(addr.sun_path) - 1);
+    if (strlen(path) >= sizeof(addr.sun_path)) { fprintf(stderr, "bgbackend --serve: socket path too long (%zu bytes max)\n", sizeof(addr.sun_path) - 1); return 1; }
+    strcpy(addr.sun_path, path);
     unlink(path);
-    if (bind(srv, (sockaddr*)&addr, sizeof addr) < 0 || listen(srv, 16) < 0) { perror("bind/listen"); return 1; }
+    const mode_t old_umask = umask(0077);          // the socket is for this user only
+    const bool bound = bind(srv, (sockaddr*)&addr, sizeof addr) == 0 && listen(srv, 16) == 0;
+    umask(old_umask);
+    if (!bound) { perror("bind/listen"); return 1; }
     printf("bgbackend serving on %s with %d GPU(s)\n", path, gpus);
     fflush(stdout);
     uint64_t calls = 0;
@@ -427,6 +471,9 @@ static int serve(const char* path, int gpus, int device0, bool chatter) {
     while (true) {
         int fd = accept(srv, nullptr, nullptr);
         if (fd < 0) { if (errno == EINTR) continue; break; }
+        timeval tv; tv.tv_sec = 30; tv.tv_usec = 0;    // a stalled client cannot block the calls behind it for ever
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
         std::string in;
         if (read_all(fd, &in)) {
             if (in == "shutdown\n") { close(fd); break; }

@@ -752,6 +752,7 @@ struct bg_ctx {
     uint64_t samples = 0; int bins = 1; uint64_t seeds[2] = {0, 0};
     bool prepared = false;
     bool per_valid = false;         // d_per holds the per-sample values of a finished job
+    bg_projector* h_stage = nullptr; cudaEvent_t ev_stage = nullptr;   // pinned staging copy of the projectors + its upload event
     bg_projector h_P[2];            // what d_P holds (a repeated prepare with the same content keeps the captured graph)
     bool phase_events = false;
     int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
@@ -812,6 +813,19 @@ extern "C" const char* bg_last_error(const bg_ctx* ctx) {
     return g_last_error.c_str();
 }
 
+extern "C" int bg_device_count(int* out) {
+    if (!out) return fail(nullptr, "bg_device_count: null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        *out = 0;
+        return fail(nullptr, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    *out = ndev;
+    return 0;
+}
+
 extern "C" int bg_init(bg_ctx** out, int device) {
     if (!out) return fail(nullptr, "bg_init: null out pointer");
     *out = nullptr;
@@ -828,8 +842,8 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) {
-        int r = fail(nullptr, "bg_init: device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+    if (prop.major != 10 || prop.minor != 0) {      // the library carries sm_100a SASS only (no PTX)
+        int r = fail(nullptr, "bg_init: device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
         delete ctx; return r;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, "cudaStreamCreate failed"); }
@@ -843,6 +857,8 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (cudaMalloc((void**)&ctx->d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_stage, 2 * sizeof(bg_projector), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 16 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_partials, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_ticket, 2 * sizeof(unsigned int)) != cudaSuccess ||
@@ -880,6 +896,8 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     }
     if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1272,22 +1290,26 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     }
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
-    if (ctx->prepared && ctx->nproj == nproj && ctx->samples == samples && ctx->bins == bins) {
-        // the job that is already prepared (same projectors, sizes and seeds): nothing to upload, the graph stays
-        bool same = true;
-        for (int j = 0; same && j < nproj; j++)
-            same = ctx->seeds[j] == seeds[j] && memcmp(&ctx->h_P[j], Ps[j], sizeof(bg_projector)) == 0;
-        if (same) { ctx->stats.h2d_bytes = 0; return 0; }
+    // the projectors go through a pinned staging copy, asynchronously on the job's stream (the kernels read d_P when
+    // they run, so a captured graph stays valid); a job of the same shape and seeds keeps its graph
+    bool same_shape = ctx->prepared && ctx->nproj == nproj && ctx->samples == samples && ctx->bins == bins;
+    for (int j = 0; same_shape && j < nproj; j++) same_shape = ctx->seeds[j] == seeds[j];
+    if (!same_shape && ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
+    bool same_P = same_shape;
+    for (int j = 0; same_P && j < nproj; j++) same_P = memcmp(&ctx->h_P[j], Ps[j], sizeof(bg_projector)) == 0;
+    ctx->stats.h2d_bytes = 0;
+    if (!same_P) {
+        if (ctx->run_seq != ctx->fin_seq) return fail(ctx, "bg_sampled_prepare: a job is still in flight");
+        CK(cudaEventSynchronize(ctx->ev_stage));         // the previous upload has left the staging buffer
+        for (int j = 0; j < nproj; j++) ctx->h_stage[j] = *Ps[j];
+        CK(cudaMemcpyAsync(ctx->d_P, ctx->h_stage, (size_t)nproj * sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
+        ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
     }
-    if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
-    for (int j = 0; j < nproj; j++)
-        CK(cudaMemcpyAsync(ctx->d_P + j, Ps[j], sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));          // the caller's projector may be a temporary
-    ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
     ctx->nproj = nproj; ctx->samples = samples; ctx->bins = bins;
     for (int j = 0; j < nproj; j++) { ctx->seeds[j] = seeds[j]; ctx->h_P[j] = *Ps[j]; }
     ctx->prepared = true; ctx->per_valid = false;
-    drop_graph(ctx);
+    if (!same_shape) drop_graph(ctx);
     return 0;
 }
 

@@ -69,6 +69,7 @@ typedef struct bg_ctx bg_ctx;
 /* Create a context on CUDA device `device`.  Replaces MPI_Init + the worker
  * "init" command (libcirc/probability.c:31-37, 184-191, 248-257). */
 int  bg_init(bg_ctx** out, int device);
+int  bg_device_count(int* out);                 /* visible sm_100 CUDA devices (checked before a multi-GPU start) */
 void bg_shutdown(bg_ctx* ctx);
 const char* bg_last_error(const bg_ctx* ctx);   /* ctx may be NULL: last global error */
 

@@ -54,6 +54,8 @@ class Emu:
         lib.emu_terms_shb.restype = C.c_int
         lib.emu_expsum_selftest.argtypes = [C.c_int, C.c_ulonglong, C.c_int]
         lib.emu_expsum_selftest.restype = C.c_int
+        lib.emu_chi_seconds.argtypes = [C.c_int]
+        lib.emu_chi_seconds.restype = C.c_double
         lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
         self.lib = lib
 

@@ -1,6 +1,8 @@
 // emu_lib.cpp — TEST INFRASTRUCTURE: runs the product's warp-level device code
 // (circuitsimulator_b200/csrc/bg_device.cuh, bg_philox.cuh) on the CPU warp emulator.
+#ifndef BG_EMU_FAST
 #define BG_COUNT_WORK 1
+#endif
 #include "cpu_warp.h"
 #include "bg_device.cuh"
 #include "bg_warp_ops.cuh"
@@ -8,6 +10,7 @@
 #include "bg_shb.cuh"
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 namespace emu {
@@ -47,6 +50,9 @@ void run(const std::function<void()>& body) {
 }
 }  // namespace emu
 
+#if defined(BG_EMU_FAST)
+struct BgWork { unsigned long long xors, rows, dimers, monomers, basis_changes, pairs; };
+#endif
 BgWork g_bg_work = {0, 0, 0, 0, 0, 0};
 int* g_bg_trace = nullptr; int g_bg_trace_n = 0, g_bg_trace_cap = 0;
 using namespace bg;
@@ -54,6 +60,7 @@ using namespace bg;
 #ifndef EMU_SHB_G
 #define EMU_SHB_G 2
 #endif
+static double g_emu_chi_seconds = 0;     // time spent in the chi loop of emu_terms_tpp (bench.py: cpu_baseline_packed)
 static int g_emu_lam_max = 4;   // checks carried as Lagrange variables (as k_pairs_tpp does; 0: every check pivoted per term)
 // Same as emu_terms, but the chi loop runs through the thread-per-pair code (bg_tpp.cuh): the
 // ambient form is produced by the warp-level code under emulation, each term is then a plain call.
@@ -104,6 +111,7 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
         }
         W work[128];
         Rows<W> rows; rows.base = work; rows.stride = 1; rows.sbase = 0; rows.sstride = 0;
+        const auto chi_t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < nterms; i++) {
             int e, p, m;
             if (many) {
@@ -116,6 +124,7 @@ static int terms_tpp(const bg_state* theta, const bg_projector* P, int project, 
             zw_add(z, e, p, m, t / 2 + 1);
             if (epm) { epm[3 * i] = e; epm[3 * i + 1] = p; epm[3 * i + 2] = m; }
         }
+        g_emu_chi_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - chi_t0).count();
     }
     if (zw_out) for (int j = 0; j < 4; j++) zw_out[j] = z.a[j];
     return alive;
@@ -301,6 +310,7 @@ int emu_expsum_selftest(int wordbits, unsigned long long seed, int trials) {
 }
 
 void emu_set_lam_max(int n) { g_emu_lam_max = n; }
+double emu_chi_seconds(int reset) { const double v = g_emu_chi_seconds; if (reset) g_emu_chi_seconds = 0; return v; }
 void emu_trace(int* buf, int cap) { g_bg_trace = buf; g_bg_trace_cap = cap; g_bg_trace_n = 0; }
 int emu_trace_len(void) { return g_bg_trace_n; }
 
