@@ -103,6 +103,9 @@ struct PairArgs {
     int32_t* epm;           // optional [n_samples][nterms][3]
     int smem_terms;         // terms staged in shared memory (0: read from global / L2)
     int tri;                // exact-norm mode: sample i meets terms j >= first_index(i)
+    int natural;            // the terms are in natural order (term_nat is the identity): tri mode, so that a sample's
+                            // terms j >= i are a contiguous range and no lane is masked off (innerprod.c:203-215 unranks
+                            // the pair index the same way)
     uint64_t first, stride; // global index of sample idx = first + idx*stride   (tri mode)
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
@@ -275,9 +278,9 @@ __global__ void __launch_bounds__(128) k_pairs(PairArgs a) {
         Zw z, z2;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
-        for (int i = i0; i < i1; i++) {
+        for (int i = (a.tri && a.natural) ? max(i0, diag_index) : i0; i < i1; i++) {
             const W term = (W)terms[i];
-            const int nat = (a.tri || a.epm) ? a.term_nat[i] : i;
+            const int nat = (!a.natural && (a.tri || a.epm)) ? a.term_nat[i] : i;
             if (a.tri && nat < diag_index) continue;
             int e, p, m;
             if (EXACT) term_H<NS>(am.f, am.Cw, am.Cpend, am.Cbeta, am.k1, a.t, term, e, p, m);
@@ -401,9 +404,9 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
         Zw z, z2;
         z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
         z2.a[0] = z2.a[1] = z2.a[2] = z2.a[3] = 0;
-        for (int g = i0; g < i1; g += 32) {
+        for (int g = (TRI && a.natural) ? max(i0, diag_index & ~31) : i0; g < i1; g += 32) {
             const int i = g + lane;
-            const int nat = (i < i1 && (TRI || a.epm)) ? a.term_nat[i] : i;
+            const int nat = (i < i1 && !a.natural && (TRI || a.epm)) ? a.term_nat[i] : i;
             if (i < i1 && !(TRI && nat < diag_index)) {
                 const unsigned group = __activemask();
                 const W term = (W)terms[i];
@@ -1195,8 +1198,9 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     unsigned long long* cnt = CNT(ctx) + 4 * ctx->cur;
     a.pair_count = cnt + 1;
     a.n_warp_routed = cnt + 2;
-    a.terms = ctx->d_terms_sorted;
+    a.terms = a.tri ? ctx->d_terms : ctx->d_terms_sorted;
     a.term_nat = ctx->d_term_nat;
+    a.natural = a.tri ? 1 : 0;
     if (!ctx->force_warp) {
         a.smem_terms = padded <= 2048 ? (int)padded : 0;
         const size_t wb = a.t <= 32 ? 4 : 8;

@@ -651,3 +651,50 @@ def test_statistical_gate_sampled_vs_exact_norm_t16(be, oracle):
         se = est.std(ddof=1) / np.sqrt(len(est))
         assert abs(est.mean() - exact) <= 3 * se, (est.mean(), exact, se)
         assert se < 0.05 * exact
+
+
+# ----------------------------------------------------------------------------- build / launch variants, multi-GPU back end
+def _backend_stream(name, samples=None, k=None):
+    txt = open(os.path.join(GOLDEN, "streams", name)).read().split()
+    if samples is not None:
+        txt[3] = str(samples)
+    if k is not None:
+        txt[6] = str(k)
+    return "\n".join(txt) + "\n"
+
+
+@pytest.mark.parametrize("env", [{"BG_KERNEL": "warp"}, {"BG_FUSE2": "0"}, {"BG_SHB": "0"}, {"BG_GRAPH": "0"},
+                                 {"BG_ITEMS_FACTOR": "1"}, {"BG_CTAS_PER_SM": "2"}],
+                         ids=lambda e: "_".join("%s=%s" % kv for kv in e.items()))
+def test_launch_variants_give_identical_sums(env):
+    """Every default-off variant on the hardware: the warp-per-pair kernel (the north-star mapping, BG_KERNEL=warp),
+    one launch sequence per projector (BG_FUSE2=0), the generic 64-bit kernel instead of the shared high-block one
+    (BG_SHB=0), no CUDA graph, other work partitions.  Per-sample sums are exact integers, so numerator and
+    denominator must agree to the last bits (only the final fp64 sum over samples depends on the order)."""
+    import circuitsimulator_b200 as bg
+    text = _backend_stream("hs_t40_k9_bit0.txt", samples=2048)
+    base = dict(BG_SEED=5)
+    num0, den0, _ = bg.run_backend(text, env=base)
+    num1, den1, _ = bg.run_backend(text, env=dict(base, **env))
+    assert abs(num1 - num0) <= 4e-16 * abs(num0) and abs(den1 - den0) <= 4e-16 * abs(den0), (num0, num1, den0, den1)
+
+
+def test_multi_gpu_backend_matches_single_gpu():
+    """bgbackend with BG_GPUS=2 (one host thread + context per GPU, in-process NCCL all-reduce): sampled path,
+    exact-norm path and the persistent server against the single-GPU answers.  Needs two visible GPUs."""
+    import torch
+    import circuitsimulator_b200 as bg
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    text = _backend_stream("hs_t40_k9_bit0.txt", samples=4096)
+    n1, d1, _ = bg.run_backend(text, env=dict(BG_SEED=5, BG_GPUS=1))
+    n2, d2, _ = bg.run_backend(text, env=dict(BG_SEED=5, BG_GPUS=2))
+    assert abs(n2 - n1) <= 1e-13 * abs(n1) and abs(d2 - d1) <= 1e-13 * abs(d1)
+    tof = open(os.path.join(GOLDEN, "streams", "toffoli_111.txt")).read()          # exact-norm path (all-reduce of 2 doubles)
+    a1, b1, _ = bg.run_backend(tof, env=dict(BG_SEED=5, BG_GPUS=1))
+    a2, b2, _ = bg.run_backend(tof, env=dict(BG_SEED=5, BG_GPUS=2))
+    assert abs(a2 - a1) <= 1e-12 * abs(a1) and abs(b2 - b1) <= 1e-12 * abs(b1)
+    assert abs(a2 / b2 - 1.0) < 1e-9
+    # more GPUs than the box has: an Error line, not a hang
+    with pytest.raises(bg.BGError):
+        bg.run_backend(text, env=dict(BG_GPUS=64), timeout=120)
