@@ -314,6 +314,21 @@ class Reference(_Api):
     def available():
         return os.path.exists(os.path.join(HERE, "_ref", "libcircref.so"))
 
+    def projector_bytes(self, P):
+        """(phaseSign.data, phaseComplex.data, xs.data, zs.data) of the reference's own struct Projector for P"""
+        cap = (P.nstabs * P.nqubits + 7) // 8 + 8
+        bufs = [(C.c_ubyte * cap)() for _ in range(4)]
+        n = self.lib.ref_projector_bytes(C.byref(P), bufs[0], bufs[1], bufs[2], bufs[3], cap)
+        assert n >= 0
+        return bufs
+
+    def L_bytes(self, t, Lrows):
+        """BitMatrix.data of the reference's k x t matrix L"""
+        cap = (len(Lrows) * t + 7) // 8 + 8
+        buf = (C.c_ubyte * cap)()
+        assert self.lib.ref_L_bytes(len(Lrows), t, u64_array(Lrows), buf, cap) >= 0
+        return buf
+
     def srand(self, seed):
         self.lib.ref_srand(seed)
 

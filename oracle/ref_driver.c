@@ -273,5 +273,28 @@ double ref_sample_from_theta(bg_state* theta, const bg_projector* P, int exact, 
     return pow(2, t) * ComplexMagSquare(ComplexMulReal(total, projfactor));
 }
 
+/* The reference's own containers as the level-2 binding sees them: a struct Projector / BitMatrix built by the
+ * reference's constructors and setters (matrix.c), handed over as raw .data byte arrays.  Copies them out so that
+ * the test can push them through bg_projector_from_bitmatrix / bg_set_decomposition_bitmatrix (matrix.c:124-131,
+ * 330-339: MSB-first, no row padding). */
+int ref_projector_bytes(const bg_projector* P, unsigned char* phase_sign, unsigned char* phase_complex,
+                        unsigned char* xs, unsigned char* zs, int cap) {
+    struct Projector* R = projector_from_packed(P);
+    const int nb_v = (P->nstabs + 7) / 8, nb_m = (P->nstabs * P->nqubits + 7) / 8;
+    if (P->nstabs == 0 || nb_m > cap) { projector_free(R); return -1; }
+    memcpy(phase_sign, R->phaseSign->data, nb_v); memcpy(phase_complex, R->phaseComplex->data, nb_v);
+    memcpy(xs, R->xs->data, nb_m); memcpy(zs, R->zs->data, nb_m);
+    projector_free(R);
+    return nb_m;
+}
+int ref_L_bytes(int k, int t, const uint64_t* rows, unsigned char* out, int cap) {
+    struct BitMatrix* L = L_from_rows(k, t, rows);
+    const int nb = (k * t + 7) / 8;
+    if (nb > cap) { BitMatrixFree(L); return -1; }
+    memcpy(out, L->data, nb);
+    BitMatrixFree(L);
+    return nb;
+}
+
 size_t ref_sizeof_state(void) { return sizeof(bg_state); }
 size_t ref_sizeof_projector(void) { return sizeof(bg_projector); }

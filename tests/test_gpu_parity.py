@@ -698,3 +698,38 @@ def test_multi_gpu_backend_matches_single_gpu():
     # more GPUs than the box has: an Error line, not a hang
     with pytest.raises(bg.BGError):
         bg.run_backend(text, env=dict(BG_GPUS=64), timeout=120)
+
+
+def test_level2_binding_reference_host_on_the_c_abi(be, reference):
+    """INTEGRATION.md level 2, built for real (oracle/Makefile: _ref/mpibackend_bg): the reference's UNMODIFIED
+    probability.c (main / master / decompose) linked against the C ABI instead of libcirc/innerprod.c, passing its own
+    struct Projector / BitMatrix byte arrays through the *_bitmatrix adapters.  It must print the numbers the drop-in
+    executable prints for the same stream and seed (sampled path, |L> path with decompose()'s L, exact-norm path),
+    and bg_set_decomposition_bitmatrix must build the same terms as the packed-row entry."""
+    import subprocess
+    import circuitsimulator_b200 as bg
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "mpibackend_bg")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mpibackend_bg not built (needs the reference tree at build time)")
+    for name, kw in [("htstack_t4.txt", {}), ("hs_t16_bit6.txt", dict(samples=512)), ("hs_t40_k9_bit0.txt", dict(samples=256)),
+                     ("toffoli_111.txt", {})]:
+        text = _backend_stream(name, **kw)
+        env = dict(os.environ, BG_SEED="11")
+        p = subprocess.run([exe, "stdin"], input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+        lines = p.stdout.decode().splitlines()
+        num2, den2 = float(lines[-2]), float(lines[-1])
+        num1, den1, _ = bg.run_backend(text, env={"BG_SEED": 11})
+        assert abs(num2 - num1) <= 1e-12 * max(abs(num1), 1e-300), (name, num1, num2)
+        assert abs(den2 - den1) <= 1e-12 * max(abs(den1), 1e-300), (name, den1, den2)
+    # the decomposition adapter on the reference's BitMatrix.data
+    t = 40
+    L = _bench_L(9, t)
+    import ctypes as C
+    be.set_decomposition(t, False, L)
+    a = be.decomposition_terms(0, 512)
+    be.set_decomposition(16, True)                          # so that the next call cannot be recognised as unchanged
+    buf = reference.L_bytes(t, L)
+    lib = bg.load_library()
+    assert lib.bg_set_decomposition_bitmatrix(be.ctx, t, 0, 9, C.cast(buf, C.POINTER(C.c_uint8))) == 0
+    b = be.decomposition_terms(0, 512)
+    assert a.tobytes() == b.tobytes()

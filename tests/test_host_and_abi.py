@@ -219,3 +219,28 @@ def test_bench_host_helpers(monkeypatch):
     broken = types.ModuleType("pynvml")                  # no NVML: the poller of the nvidia-smi binary is used
     monkeypatch.setitem(sys.modules, "pynvml", broken)
     assert bench.ClockSampler(0).nvml is None
+
+
+def test_bitmatrix_adapter_on_the_reference_layout(reference):
+    """bg_projector_from_bitmatrix (the adapter of the level-2 binding) fed with the .data byte
+    arrays of a struct Projector that the REFERENCE's own constructors built (BitVector / BitMatrix, MSB-first,
+    no row padding: matrix.c:124-131, 330-339; comms.h:4-11) must give back the packed projector."""
+    import ctypes as C
+    import numpy as np
+    bg = _built()
+    lib = bg.load_library()
+    from oracle.oracle import Projector as OProj
+    rs = np.random.RandomState(2)
+    for t, n in [(1, 1), (4, 3), (7, 5), (16, 11), (33, 20), (40, 29), (63, 7), (64, 128)]:
+        ph = [int(rs.randint(0, 4)) for _ in range(n)]
+        xs = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) | ((int(rs.randint(0, 4)) << 62) & ((1 << t) - 1)) for _ in range(n)]
+        zs = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) | ((int(rs.randint(0, 4)) << 62) & ((1 << t) - 1)) for _ in range(n)]
+        P = OProj.make(t, ph, xs, zs)
+        sign, cplx, bx, bz = reference.projector_bytes(P)
+        out = bg.Projector()
+        rc = lib.bg_projector_from_bitmatrix(C.byref(out), n, t, C.cast(sign, C.POINTER(C.c_uint8)), C.cast(cplx, C.POINTER(C.c_uint8)),
+                                             C.cast(bx, C.POINTER(C.c_uint8)), C.cast(bz, C.POINTER(C.c_uint8)))
+        assert rc == 0
+        assert (out.nstabs, out.nqubits) == (n, t)
+        assert [out.phase[i] for i in range(n)] == ph
+        assert [out.xs[i] for i in range(n)] == xs and [out.zs[i] for i in range(n)] == zs
