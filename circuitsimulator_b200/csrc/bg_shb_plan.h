@@ -15,7 +15,7 @@
 #include <vector>
 
 #define SHB_MAXH 12        // high variables taken from the term (t - 32)
-#define SHB_MAXLAM 4       // parity checks of theta carried along as Lagrange variables
+#define SHB_MAXLAM 6       // parity checks of theta carried along as Lagrange variables (more: generic kernel)
 #define SHB_MAXHT (SHB_MAXH + SHB_MAXLAM)
 #ifndef SHB_RELOC
 #define SHB_RELOC 4        // leftover high variables a thread can relocate to free low slots (host-checked)

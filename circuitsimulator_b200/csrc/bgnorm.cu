@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
 #ifndef SHB_G
 #define SHB_G 2
 #endif
-#define SHB_CLASS_WORDS (32 + SHB_MAXHT)
+#define SHB_CLASS_WORDS ((32 + SHB_MAXHT + 3) & ~3)          // 16-byte aligned: the reduced rows are read with LDS.128
 #define SHB_WARP_WORDS (SHB_G * SHB_CLASS_WORDS)
 __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
