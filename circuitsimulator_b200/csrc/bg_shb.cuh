@@ -76,20 +76,19 @@ BG_DEV void shb_reduce(ShbForm f, uint32_t Eh, uint32_t& Lout, uint32_t& Rout, S
 
 
 // ---- relabelling a sample (natural variable order, as k_prepare stores it) into a ShbForm
-struct ShbPerm { int nh, nsw; uint8_t swp[SHB_MAXH], swq[SHB_MAXH]; };
+struct ShbPerm { int nh, nsw; uint8_t swp[SHB_MAXH], swq[SHB_MAXH]; uint8_t iperm[64]; };
 
+// every swap exchanges a position p < 32 with a position q >= 32: bit p of the low word <-> bit q - 32 of the high word
 BG_DEV uint64_t shb_perm_word(uint64_t w, const ShbPerm& pm) {
+    uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
     for (int i = 0; i < pm.nsw; i++) {
-        const uint64_t x = ((w >> pm.swp[i]) ^ (w >> pm.swq[i])) & 1ull;
-        w ^= (x << pm.swp[i]) | (x << pm.swq[i]);
+        const uint32_t p = pm.swp[i], q = pm.swq[i] - 32u;
+        const uint32_t x = ((lo >> p) ^ (hi >> q)) & 1u;
+        lo ^= x << p; hi ^= x << q;
     }
-    return w;
+    return ((uint64_t)hi << 32) | lo;
 }
-BG_DEV int shb_perm_index(int c, const ShbPerm& pm) {            // the variable that sits at position c
-    int o = c;
-    for (int i = 0; i < pm.nsw; i++) { if (c == pm.swp[i]) o = pm.swq[i]; if (c == pm.swq[i]) o = pm.swp[i]; }
-    return o;
-}
+BG_DEV int shb_perm_index(int c, const ShbPerm& pm) { return pm.iperm[c]; }      // the variable that sits at position c
 
 // J: t ambient rows, Cw / Cpend / Cbeta: the parity checks (row slots in Cpend), natural labels.  Warp-cooperative.
 // Returns the number of checks (<= SHB_MAXLAM, the caller's routing guarantees it); they become the high

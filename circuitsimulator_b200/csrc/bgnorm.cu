@@ -736,7 +736,7 @@ struct bg_ctx {
     long long* d_zw2 = nullptr; size_t zw2_cap = 0;
     double* d_per = nullptr; size_t per_cap = 0;
     double* d_per2 = nullptr; size_t per2_cap = 0;
-    int ctas_per_sm = 8, items_factor = 8;
+    int ctas_per_sm = 8, items_factor = 8; bool items_factor_set = false;
 #if defined(BG_ELIM_FOLD)
     int lam_max = 0;
 #else
@@ -878,7 +878,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
     if (const char* e8 = getenv("BG_SHB")) ctx->use_shb = atoi(e8) != 0;
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
-    if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) ctx->items_factor = v; }
+    if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) { ctx->items_factor = v; ctx->items_factor_set = true; } }
     *out = ctx;
     return 0;
 }
@@ -1173,11 +1173,13 @@ template <typename W, bool MANYC> static int launch_tpp_w(bg_ctx* ctx, const Pai
 static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     if (a.n_samples <= 0) return 0;
     const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
-    const int want_items = resident_warps * ctx->items_factor;
     // the last quarter of the (popcount-sorted, i.e. cheapest) terms goes out in 32-term items
     // (only when samples are scarce: with plenty of samples the big items balance by themselves)
     const bool shb = ctx->shb_plan.ok && !a.tri && !ctx->force_warp && (((size_t)a.nterms + 1) & ~(size_t)1) <= 2048;
     const int gran = shb ? 32 * SHB_G : 32;                    // items are whole groups of terms
+    // k_pairs_shb relabels the sample once per item (about half a batch of work): one item per resident warp is
+    // enough there (measured at 2 x 8192 samples: 0.80 ms with 1, 0.92 ms with 8 items per warp)
+    const int want_items = resident_warps * (shb && !ctx->items_factor_set ? 1 : ctx->items_factor);
     const int tail_terms = (a.nterms >= 128 && a.n_samples < want_items) ? (((a.nterms / 4) + gran - 1) / gran * gran) : 0;
     a.tail_start = a.nterms - tail_terms;
     a.tail_size = gran;
@@ -1216,6 +1218,7 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
             b.terms = ctx->d_terms_shb; b.term_nat = ctx->d_term_nat_shb;
             b.shb.nh = ctx->shb_plan.nh; b.shb.nsw = ctx->shb_plan.nsw;
             for (int i = 0; i < SHB_MAXH; i++) { b.shb.swp[i] = ctx->shb_plan.swp[i]; b.shb.swq[i] = ctx->shb_plan.swq[i]; }
+            for (int i = 0; i < 64; i++) b.shb.iperm[i] = ctx->shb_plan.iperm[i];
             const size_t smem = (size_t)b.smem_terms * 8 + (size_t)tw * SHB_WARP_WORDS * 4 + (size_t)32 * 32 * tw * 4;
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_pairs_shb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;

@@ -254,6 +254,7 @@ int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int
         __syncwarp();
         ShbPerm pm; pm.nh = pl.nh; pm.nsw = pl.nsw;
         for (int i = 0; i < SHB_MAXH; i++) { pm.swp[i] = pl.swp[i]; pm.swq[i] = pl.swq[i]; }
+        for (int i = 0; i < 64; i++) pm.iperm[i] = pl.iperm[i];
         ShbForm f;
         const int nlam = shb_load(Jrows, Cwrows, am.Cpend, am.Cbeta, am.f.D1, am.f.D2, am.f.Q, t, pm, f);
         const uint32_t lam_bits = ((1u << nlam) - 1u) << pm.nh;
