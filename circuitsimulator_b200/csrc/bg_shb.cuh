@@ -93,6 +93,9 @@ BG_DEV int shb_perm_index(int c, const ShbPerm& pm) { return pm.iperm[c]; }     
 // J: t ambient rows, Cw / Cpend / Cbeta: the parity checks (row slots in Cpend), natural labels.  Warp-cooperative.
 // Returns the number of checks (<= SHB_MAXLAM, the caller's routing guarantees it); they become the high
 // variables nh .. nh+nlam-1 with D = 4 beta.
+// Every lane relabels exactly two words: its low row, and one more — lane j < nh the high row j, lane nh + j the
+// check j, lanes 30 / 31 the vectors D1 / D2 (nh + SHB_MAXLAM <= 30) — so the bit swaps are paid twice per item,
+// not once per word.
 BG_DEV int shb_load(const uint64_t* J, const uint64_t* Cw, uint64_t Cpend, uint64_t Cbeta, uint64_t D1, uint64_t D2,
                     uint32_t Q, int t, const ShbPerm& pm, ShbForm& f) {
     const int lane = bg_lane();
@@ -100,24 +103,31 @@ BG_DEV int shb_load(const uint64_t* J, const uint64_t* Cw, uint64_t Cpend, uint6
     const uint64_t maskt = t >= 64 ? ~0ull : ((1ull << t) - 1ull);
     const uint32_t maskh = (1u << nh) - 1u;
     f.L = (uint32_t)shb_perm_word(J[shb_perm_index(lane, pm)] & maskt, pm);
-    int nlam = 0;
-    uint64_t hw = 0;
-    uint32_t beta_bits = 0;
-    if (lane < nh) hw = shb_perm_word(J[shb_perm_index(32 + lane, pm)] & maskt, pm);
-    for (uint64_t pend = Cpend; pend && nlam < SHB_MAXLAM; pend &= pend - 1ull) {
+    int nlam = __popcll(Cpend);
+    if (nlam > SHB_MAXLAM) nlam = SHB_MAXLAM;
+    // this lane's second word
+    uint64_t src = 0;
+    uint32_t my_beta = 0;
+    if (lane < nh) src = J[shb_perm_index(32 + lane, pm)];
+    else if (lane < nh + nlam) {
+        uint64_t pend = Cpend;
+        for (int j = nh; j < lane; j++) pend &= pend - 1ull;           // drop the checks of the lanes before this one
         const int b = __ffsll((long long)pend) - 1;
-        if (lane == nh + nlam) hw = shb_perm_word(Cw[b] & maskt, pm);
-        beta_bits |= (uint32_t)((Cbeta >> b) & 1ull) << nlam;
-        nlam++;
-    }
-    f.R = (uint32_t)hw; f.S = (uint32_t)(hw >> 32) & maskh;
+        src = Cw[b];
+        my_beta = (uint32_t)((Cbeta >> b) & 1ull);
+    } else if (lane == 30) src = D1;
+    else if (lane == 31) src = D2;
+    const uint64_t hw = shb_perm_word(src & maskt, pm);
+    const uint32_t hlo = (uint32_t)hw, hhi = (uint32_t)(hw >> 32);
+    const bool high = lane < nh + nlam;
+    f.R = high ? hlo : 0u; f.S = high ? (hhi & maskh) : 0u;
     for (int j = 0; j < nlam; j++) {                             // column nh + j of the high rows = check j on the high variables
         const uint32_t sl = __shfl_sync(BG_FULL, f.S, nh + j);
         if (lane < nh) f.S |= ((sl >> lane) & 1u) << (nh + j);
     }
-    const uint64_t d1 = shb_perm_word(D1 & maskt, pm), d2 = shb_perm_word(D2 & maskt, pm);
-    f.D1lo = (uint32_t)d1; f.D1hi = (uint32_t)(d1 >> 32) & maskh;
-    f.D2lo = (uint32_t)d2; f.D2hi = ((uint32_t)(d2 >> 32) & maskh) | (beta_bits << nh);
+    const uint32_t beta_bits = __ballot_sync(BG_FULL, my_beta != 0u);   // bit nh + j = right-hand side of check j
+    f.D1lo = __shfl_sync(BG_FULL, hlo, 30); f.D1hi = __shfl_sync(BG_FULL, hhi, 30) & maskh;
+    f.D2lo = __shfl_sync(BG_FULL, hlo, 31); f.D2hi = (__shfl_sync(BG_FULL, hhi, 31) & maskh) | beta_bits;
     f.Q = Q;
     return nlam;
 }

@@ -110,6 +110,10 @@ struct PairArgs {
     unsigned long long* pair_count;   // total pairs evaluated (for the throughput metric)
     const unsigned long long* n_warp_routed;   // samples routed to the warp-per-pair kernel
     ShbPerm shb;                               // k_pairs_shb: the relabelling of the variables (bg_shb_plan.h)
+    // k_pairs_shb's work items: samples [0, split_from) are one item each (relabelling a sample costs half a batch),
+    // the rest — about one wave of resident warps, handed out last — go out in `pieces` items of `piece` terms,
+    // so that the last wave is short
+    int split_from, piece, pieces;
     int lam_max;                               // samples with at most this many parity checks carry them as Lagrange
                                                // variables t .. t+lam_max-1 of the ambient form (t + lam_max <= word size)
 };
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
     uint32_t* my_red = s_warp + h * SHB_CLASS_WORDS;
     uint32_t* my_left = my_red + 32;
 
-    const unsigned long long n_items = (unsigned long long)a.n_samples * (unsigned long long)(a.chunks_per_sample + a.tail_chunks);
+    const unsigned long long n_items = (unsigned long long)a.split_from + (unsigned long long)(a.n_samples - a.split_from) * (unsigned)a.pieces;
     const int sh_ = t / 2 + 1;
     unsigned long long my_pairs = 0;
     while (true) {
@@ -485,7 +489,13 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
         item = __shfl_sync(BG_FULL, item, 0);
         if (item >= n_items) break;
         int idx, i0, i1;
-        item_range(a, item, idx, i0, i1);
+        if (item < (unsigned long long)a.split_from) { idx = (int)item; i0 = 0; i1 = a.nterms; }
+        else {
+            const uint32_t j = (uint32_t)(item - (unsigned long long)a.split_from);      // < 2^30 x pieces (host-checked)
+            const uint32_t s_ = j / (uint32_t)a.pieces;
+            idx = a.split_from + (int)s_;
+            i0 = (int)(j - s_ * (uint32_t)a.pieces) * a.piece; i1 = min(a.nterms, i0 + a.piece);
+        }
         const SampleRec* r = &a.recs[idx];
         if (r->alive != ROUTE_SHB) continue;
         if (i0 >= i1) continue;
@@ -1219,6 +1229,18 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
             b.shb.nh = ctx->shb_plan.nh; b.shb.nsw = ctx->shb_plan.nsw;
             for (int i = 0; i < SHB_MAXH; i++) { b.shb.swp[i] = ctx->shb_plan.swp[i]; b.shb.swq[i] = ctx->shb_plan.swq[i]; }
             for (int i = 0; i < 64; i++) b.shb.iperm[i] = ctx->shb_plan.iperm[i];
+            {   // whole samples first; the last wave's worth of samples in pieces
+                const int groups = b.nterms / gran;
+                const int rw = ctx->sm_count * 30;                               // resident warps of k_pairs_shb (10 CTAs x 3 warps)
+                int pieces = 4;
+                while ((long long)std::min(b.n_samples, rw) * pieces < 2LL * rw && pieces < groups) pieces *= 2;
+                pieces = std::max(1, std::min(pieces, groups));
+                b.piece = (groups + pieces - 1) / pieces * gran;
+                b.pieces = (b.nterms + b.piece - 1) / b.piece;
+                b.split_from = std::max(0, b.n_samples - rw);
+                if ((long long)(b.n_samples - b.split_from) * b.pieces >= (1LL << 31)) return fail(ctx, "k_pairs_shb: too many work items");
+                if (ctx->items_factor_set) { b.split_from = 0; }                 // BG_ITEMS_FACTOR: every sample in pieces
+            }
             const size_t smem = (size_t)b.smem_terms * 8 + (size_t)tw * SHB_WARP_WORDS * 4 + (size_t)32 * 32 * tw * 4;
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_pairs_shb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
