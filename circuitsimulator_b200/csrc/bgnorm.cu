@@ -1482,13 +1482,22 @@ extern "C" int bg_sampled_run(bg_ctx* ctx) {
     return 0;
 }
 
-// the reference's comparator (innerprod.c:17-19): the double difference truncated to int
+// Median of the bin means (multiSampledProjector, innerprod.c:23-41: even count -> mean of the middle two).
+// The reference sorts with a comparator that truncates the double difference to int (innerprod.c:17-19): bin
+// means closer than 1.0 — always, for these norms — compare equal, so its qsort leaves them in an order that is
+// libc's business and "the median" is whatever sits in the middle.  The default here is a consistent ordering
+// (the median the estimator is meant to take); BG_REF_MEDIAN=1 reproduces the reference's call for comparison.
 static int ref_cmpfunc(const void* a, const void* b) { return (int)(*(const double*)a - *(const double*)b); }
+static int median_cmpfunc(const void* a, const void* b) {
+    const double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
 
-static double median_like_reference(std::vector<double>& v) {
+static double median_of_bins(std::vector<double>& v) {
     const int bins = (int)v.size();
     if (bins == 1) return v[0];
-    qsort(v.data(), bins, sizeof(double), ref_cmpfunc);
+    static const bool ref_order = getenv("BG_REF_MEDIAN") && atoi(getenv("BG_REF_MEDIAN")) != 0;
+    qsort(v.data(), bins, sizeof(double), ref_order ? ref_cmpfunc : median_cmpfunc);
     if (bins % 2 == 1) return v[(bins - 1) / 2];
     return (v[bins / 2] + v[bins / 2 - 1]) / 2;
 }
@@ -1534,7 +1543,7 @@ static int sampled_finish_n(bg_ctx* ctx, double* out) {
     for (int pj = 0; pj < ctx->nproj && !rc; pj++) {
         std::vector<double> v(ctx->bins);
         for (int b = 0; b < ctx->bins; b++) v[b] = HOUT(ctx)[4 * pj + b] / (double)ctx->samples;   // total/samples (innerprod.c:83)
-        out[pj] = median_like_reference(v);
+        out[pj] = median_of_bins(v);
     }
     ctx->slot = 0;
     return rc;
@@ -1582,7 +1591,7 @@ extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samp
     ctx->stats.prepare_ms = prep_ms; ctx->stats.pairs_ms = pair_ms;
     ctx->stats.d2h_bytes = bins * sizeof(double);
     ctx->per_valid = true;
-    *out = median_like_reference(v);
+    *out = median_of_bins(v);
     return 0;
 }
 
