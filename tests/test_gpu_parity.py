@@ -735,3 +735,33 @@ def test_level2_binding_reference_host_on_the_c_abi(be, reference):
     assert lib.bg_set_decomposition_bitmatrix(be.ctx, t, 0, 9, C.cast(buf, C.POINTER(C.c_uint8))) == 0
     b = be.decomposition_terms(0, 512)
     assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("t,k", [(33, 9), (36, 9), (40, 9), (40, 10), (40, 12), (44, 9), (44, 11)])
+def test_shared_high_block_kernel_equals_generic_kernel(t, k):
+    """k_pairs_shb against the generic 64-bit kernel (BG_SHB=0) on the same device-drawn thetas, per-sample values
+    bit for bit (both accumulate exact integers), for several random decompositions per (t, k): every width the plan
+    covers (1 to 12 shared variables), class sizes 32 and more, and whatever the plan search makes of each L —
+    including "no plan", where both contexts run the generic kernel."""
+    import circuitsimulator_b200 as bg
+    a = bg.Backend(0)
+    os.environ["BG_SHB"] = "0"
+    try:
+        b = bg.Backend(0)
+    finally:
+        del os.environ["BG_SHB"]
+    try:
+        rs = np.random.RandomState(100 * t + k)
+        P, _ = _random_projector(rs, t, 24)
+        for trial in range(3):
+            L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+            a.set_decomposition(t, False, L)
+            b.set_decomposition(t, False, L)
+            th = a.random_states(t, 7 + trial, 0, 0, 192)
+            ra = a.sampled_norm_from_states(P, th, project=True)
+            rb = b.sampled_norm_from_states(P, th, project=True)
+            assert np.array_equal(ra["per_sample"], rb["per_sample"]), (t, k, trial)
+            assert ra["per_sample"].max() > 0
+    finally:
+        a.close()
+        b.close()
