@@ -462,7 +462,7 @@ def cpu_baseline_packed(cfgname, per_core=300):
         return {"value": pairs / chi_busy, "unit": "inner products/s", "cores": cores, "kind": "port",
                 "value_with_theta_draw_and_projection_under_the_warp_emulator": pairs / busy,
                 "sample": "%d processes x %d samples x 1 projector x all terms; %.2f s in the chi loop per process (k_pairs_tpp's "
-                          "thread-per-pair algorithm, bg_tpp.cuh compiled for the host with -O3 -march=native, scalar; the per-sample "
+                          "thread-per-pair algorithm, bg_tpp.cuh compiled for the host with -O3 -march=x86-64-v3, scalar; the per-sample "
                           "theta draw + projection runs under the 32-fibre warp emulator and is timed separately: %.2f s in all)"
                           % (cores, per_core, chi_busy, busy)}
     except Exception as ex:
