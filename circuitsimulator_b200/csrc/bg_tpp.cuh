@@ -873,27 +873,44 @@ BG_HD bool t_oddblock64(const Rows<uint64_t>& J, uint32_t& El, uint32_t& Eh, uin
 // probability 0.29 / 0.29 / 0.19 / 0.11 / 0.06).  The blocked rounds run only while more than two are left; one or
 // two variables are finished in closed form (a monomer: factor 2 or 0; a coupled pair: a dimer; an uncoupled pair: two
 // monomers) — one row load, no pass.
-BG_HD void t_eventail32(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D2, uint32_t& cnt2, uint32_t& neg0, uint32_t& z0) {
-    if (tpopc(E) > 2) {
+BG_HD void t_eventail32(const Rows<uint32_t>& J, uint32_t& E, uint32_t D1, uint32_t& D2, uint32_t& Q, uint32_t& cnt, uint32_t& cnt2,
+                         uint32_t& neg0, uint32_t& z0) {
+    if (tpopc(E) > 2) {                                  // only even variables are left here (the odd phase ran out of odd ones)
         uint32_t Js = 0, neg1 = 0, z1 = 0;
         while (tpopc(E) > 2) t_block32<false>(J, E, D2, Js, cnt2, neg0, neg1, z0, z1, 1u, TPend<uint32_t>());
         neg0 &= 1u; z0 &= 1u;
     }
     if (E != 0u) {
+        // one or two variables of ANY kind (the odd phase stops at two): sum out an odd one first (rank-one step on a
+        // single neighbour), then the other alone
         const uint32_t a = (uint32_t)thighest(E);
         const uint32_t ba = 1u << a, bb = E ^ ba;                       // bb: the other variable, if any
-        const bool d2a = (D2 & ba) != 0u, d2b = (D2 & bb) != 0u;
         const bool coupled = (J.get((int)a) & bb) != 0u;
-        if (coupled) { neg0 ^= (d2a && d2b) ? 1u : 0u; cnt2 += 1u; }
-        else { z0 |= (d2a || d2b) ? 1u : 0u; cnt2 += bb ? 2u : 1u; }
-        BG_WORK(dimers, coupled ? 1 : 0); BG_WORK(monomers, coupled ? 0 : (bb ? 2 : 1));
+        const bool oa = (D1 & ba) != 0u, ob = (D1 & bb) != 0u;
+        const bool d2a = (D2 & ba) != 0u, d2b = (D2 & bb) != 0u;
+        if (!oa && !ob) {
+            if (coupled) { neg0 ^= (d2a && d2b) ? 1u : 0u; cnt2 += 1u; }
+            else { z0 |= (d2a || d2b) ? 1u : 0u; cnt2 += bb ? 2u : 1u; }
+            BG_WORK(dimers, coupled ? 1 : 0); BG_WORK(monomers, coupled ? 0 : (bb ? 2 : 1));
+        } else {
+            const bool first_a = oa;                                    // the odd variable that goes first
+            const bool negp = first_a ? d2a : d2b;                      // D = 6: d = -1
+            Q += negp ? 7u : 1u; cnt += 1u;
+            if (bb) {
+                bool oq = first_a ? ob : oa, d2q = first_a ? d2b : d2a;
+                if (coupled) { d2q = d2q != (oq != !negp); oq = !oq; }  // D_q -= 2d: D2_q ^= (d = +1 ? ~D1_q : D1_q), D1_q ^= 1
+                if (oq) { Q += d2q ? 7u : 1u; cnt += 1u; }
+                else { z0 |= d2q ? 1u : 0u; cnt2 += 1u; }
+            }
+            BG_WORK(monomers, bb ? 2 : 1);
+        }
         E = 0u;
     }
 }
 
 // the steps of the odd phase: blocks of 8 while any lane of the warp has more than 4 variables left
 BG_HD void t_oddphase(const Rows<uint32_t>& J, uint32_t& E, uint32_t& D1, uint32_t& D2, uint32_t& Q, uint32_t& cnt) {
-    while ((D1 & E) != 0u) {
+    while ((D1 & E) != 0u && tpopc(E) > 2) {            // one or two variables left: closed form (t_eventail32)
         if (T_WARP_ANY(tpopc(E) > 4)) t_oddblock32<8>(J, E, D1, D2, Q, cnt);
         else t_oddblock32<4>(J, E, D1, D2, Q, cnt);
     }
@@ -905,7 +922,7 @@ BG_HD void t_expsum_odd(const Rows<uint32_t>& J, TF<uint32_t>& f, int& eps, int&
     uint32_t E = f.A, D1 = f.D1, D2 = f.D2, Q = f.Q, cnt = 0;
     t_oddphase(J, E, D1, D2, Q, cnt);
     uint32_t cnt2 = 0, neg0 = 0, neg1 = 0, z0 = 0, z1 = 0;
-    t_eventail32(J, E, D2, cnt2, neg0, z0);              // what is left has D in {0,4}
+    t_eventail32(J, E, D1, D2, Q, cnt, cnt2, neg0, z0);  // even variables, or at most two of any kind
     eps = z0 ? 0 : 1;
     p = (int)cnt + 2 * (int)cnt2;
     m = (int)((Q + 4u * neg0) & 7u);
@@ -925,7 +942,7 @@ BG_HD void t_expsum_odd(const Rows<uint64_t>& J, TF<uint64_t>& f, int& eps, int&
         Jl.base = reinterpret_cast<uint32_t*>(J.base); Jl.stride = 2 * J.stride;
         Jl.sbase = J.sbase; Jl.sstride = J.sstride;
         t_oddphase(Jl, El, D1l, D2l, Q, cnt);
-        t_eventail32(Jl, El, D2l, cnt2, neg0, z0);
+        t_eventail32(Jl, El, D1l, D2l, Q, cnt, cnt2, neg0, z0);
     } else {                                             // even variables >= 32 are left and nothing odd: 64-bit rounds
         uint64_t E = t_mk64(El, Eh), D2 = t_mk64(D2l, D2h), Js = 0;
         TPend<uint64_t> pd; pd.M1 = pd.V1 = pd.M2 = pd.V2 = 0;
