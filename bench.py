@@ -368,6 +368,24 @@ def other_configs(ctx, bg, lop3_peak, skip):
     return out
 
 
+def stop_server(srv, sock):
+    """the server's own shutdown message (bgbackend.cpp: serve), over its Unix socket"""
+    import socket
+    try:
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.settimeout(10)
+        c.connect(sock)
+        c.sendall(b"shutdown\n")
+        c.shutdown(socket.SHUT_WR)
+        c.close()
+    except Exception:
+        pass
+    try:
+        srv.wait(timeout=15)
+    except Exception:
+        srv.kill()
+
+
 def probability_seconds(t, samples, k, exact, Gd, Hd, gpus):
     """BASELINE metric, second half: wall seconds of one probability() back-end evaluation as the unmodified front
     end performs it (libcirc/probability.py:237-312: spawn the back end, write the token stream, read the two
@@ -401,16 +419,61 @@ def probability_seconds(t, samples, k, exact, Gd, Hd, gpus):
             out["served"] = min(ts[1:])
             out["served_all"] = ts
         finally:
-            try:
-                bg.run_backend("shutdown\n", env={"BG_SERVER": sock}, timeout=20)
-            except Exception:
-                pass
-            try:
-                srv.wait(timeout=20)
-            except Exception:
-                srv.kill()
+            stop_server(srv, sock)
     except Exception as ex:                              # never fail the bench line because of this leg
         out["error"] = repr(ex)[:300]
+    return out
+
+
+def sample_qubits_seconds(gpus):
+    """BASELINE config 5, first half: sampleQubits(phaseEstimation.circ, "MMM_") — the chain-rule weak simulation of
+    libcirc/sample.py:32-83: one probability() call per sampled qubit (t=33, |L> k=8, 16384 samples), each conditioned on
+    the outcomes so far, P0 = P / Psofar, then a draw.  The front end's calls were written with file= for every outcome
+    prefix (tests/golden/make_fixtures.py); here the chain is replayed against `bgbackend --serve` the way
+    recursiveSample walks it.  Returns wall seconds for the whole sample (3 probability() calls) and the outcome."""
+    import random
+    import tempfile
+    import circuitsimulator_b200 as bg
+    meta = json.load(open(os.path.join(STREAMS, "meta.json"))).get("phase_estimation_chain")
+    if not meta:
+        return None
+    out = {"gpus": gpus, "circuit": "circuits/phaseEstimation.circ MMM_ (t=33, k=8, samples=16384 per projector)"}
+    env = {"BG_GPUS": gpus, "BG_SEED": 11}
+    sock = os.path.join(tempfile.mkdtemp(prefix="bgsq"), "s")
+    e = dict(os.environ); e.update({k_: str(v) for k_, v in env.items()})
+    try:
+        srv = subprocess.Popen([bg.BACKEND_PATH, "--serve", sock], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    except Exception as ex:
+        return {"error": repr(ex)[:300]}
+    try:
+        srv.stdout.readline()
+        cenv = dict(env); cenv["BG_SERVER"] = sock
+        runs = []
+        for rep in range(4):
+            rnd = random.Random(5)
+            t0 = time.perf_counter()
+            prefix, psofar, calls = "", 1.0, 0
+            for _q in meta["qubits"]:
+                ent = meta["streams"].get(prefix + "0")
+                if ent is None:                       # the front end would have answered this call itself
+                    break
+                text = open(os.path.join(STREAMS, ent["stream"])).read()
+                num, den, _lines = bg.run_backend(text, env=cenv, timeout=300)
+                calls += 1
+                prob = 0.0 if num == 0 else 2.0 ** ent["v_minus_u"] * num / den       # probability.py:320-326
+                p0 = prob / psofar
+                bit = 0 if rnd.random() < p0 else 1
+                psofar = p0 if bit == 0 else 1.0 - p0                                  # sample.py:57, 83
+                prefix += str(bit)
+            runs.append((time.perf_counter() - t0, prefix, calls))
+        out["seconds"] = min(r[0] for r in runs[1:])
+        out["seconds_all"] = [r[0] for r in runs]
+        out["sample"] = runs[-1][1]
+        out["probability_calls"] = runs[-1][2]
+    except Exception as ex:
+        out["error"] = repr(ex)[:300]
+    finally:
+        stop_server(srv, sock)
     return out
 
 
@@ -648,6 +711,8 @@ def main():
     barrier()
     if rank == 0 and not args.no_probability:
         prob_s = probability_seconds(t, samples, k, exact, Gd, Hd, world)
+        if prob_s is not None:
+            prob_s["sample_qubits_phase_estimation"] = sample_qubits_seconds(world)
     barrier()
 
     if rank == 0:

@@ -325,6 +325,37 @@ def streams():
     except Exception as e:     # noqa
         print("phaseEstimation skipped:", e)
 
+    # config 5, whole: sampleQubits(phaseEstimation.circ, "MMM_") makes one probability() call per sampled qubit, each
+    # conditioned on the outcomes before it (libcirc/sample.py:32-83).  sampleQubits disables file= mode, so the calls it
+    # would make are written here one by one for EVERY outcome prefix (1 + 2 + 4 streams); bench.py replays the chain
+    # against the back end exactly as recursiveSample does (P0 = P / Psofar, then a draw).  When the measurement dict is
+    # not empty, sampleQubits first asks for the probability of the constraints with exact=True (sample.py:37-42): those
+    # are the *_given streams.
+    try:
+        comp = compileCircuit(fname="circuits/phaseEstimation.circ")
+        cfg5 = {"samples": 16384, "k": 8, "exact": False, "forceSample": True}
+        chain = {}
+        for nq in range(3):
+            for prefix in range(1 << nq):
+                bits = [(prefix >> (nq - 1 - j)) & 1 for j in range(nq)]
+                measure = {j: b for j, b in enumerate(bits)}
+                measure[nq] = 0
+                name = "phase_estimation_chain_%s0.txt" % "".join(map(str, bits))
+                np.random.seed(50 + 8 * nq + prefix)
+                if _stream(probability, comp, measure, cfg5, os.path.join(out, name)):
+                    # probability() returns 2^(v-u) * numerator / denominator (probability.py:320-326): u, v are how many
+                    # generators truncate() removed from G and H (probability.py:93-94) — host-side, not in the stream
+                    from libcirc.compile import projectors as _pj
+                    Gp, Hp, n_, t_ = _pj.projectors(comp, dict(measure), verbose=False, x=None, y=None)
+                    u_ = _pj.truncate(n_, Gp)[1]
+                    v_ = _pj.truncate(n_, Hp)[1]
+                    chain["".join(map(str, bits)) + "0"] = {"stream": name, "v_minus_u": int(v_ - u_)}
+        meta["phase_estimation_chain"] = {"streams": chain, "qubits": [0, 1, 2],
+                                          "note": "key = outcomes so far + the 0 being asked for; a missing key means the "
+                                                  "front end answered that call itself (probability.py:111-138)"}
+    except Exception as e:     # noqa
+        print("phaseEstimation chain skipped:", e)
+
     json.dump(meta, open(os.path.join(out, "meta.json"), "w"), indent=1, sort_keys=True)
     os.chdir(ROOT)
 

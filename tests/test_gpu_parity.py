@@ -765,3 +765,24 @@ def test_shared_high_block_kernel_equals_generic_kernel(t, k):
     finally:
         a.close()
         b.close()
+
+
+def test_phase_estimation_chain_approaches_the_exact_distribution():
+    """BASELINE config 5 end to end: the probability() calls sampleQubits makes on circuits/phaseEstimation.circ
+    (one per sampled qubit, conditioned on the outcomes before it: libcirc/sample.py:32-83), written by the unmodified
+    front end, through the drop-in back end.  A state-vector simulation of the 4-qubit circuit gives
+    P(q0=0) = 0.92678, P(q0=0,q1=0) = 0.21339, P(q0=0,q1=1,q2=0) = 0.5, P(q0=1,q1=0) = 0.03661, and 0 for 000 / 100 /
+    110; with the |L> approximation at k = 14 (t = 33) the sampled estimates must sit within 0.03 of them — an
+    end-to-end check of decomposition, projection, inner products and normalisation that does not involve the oracle."""
+    import json
+    import circuitsimulator_b200 as bg
+    S = os.path.join(GOLDEN, "streams")
+    meta = json.load(open(os.path.join(S, "meta.json")))["phase_estimation_chain"]["streams"]
+    exact = {"0": 0.9267766952966369, "00": 0.21338834764831827, "010": 0.5, "000": 0.0,
+             "10": 0.03661165235168153, "100": 0.0, "110": 0.0}
+    for key, ent in sorted(meta.items()):
+        txt = open(os.path.join(S, ent["stream"])).read().split()
+        txt[6] = "14"
+        num, den, _ = bg.run_backend("\n".join(txt) + "\n", env={"BG_SEED": 3})
+        p = 0.0 if num == 0 else 2.0 ** ent["v_minus_u"] * num / den
+        assert abs(p - exact[key]) < 0.03, (key, p, exact[key])
