@@ -1069,7 +1069,7 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
         CK(cudaStreamSynchronize(ctx->stream));       // the host vectors go out of scope
     }
     ctx->shb_plan = ShbPlan();
-    if (!exact && ctx->use_shb && !ctx->force_warp && t > 32 && t <= 32 + SHB_MAXH && chi >= 32 * SHB_G && chi % (32 * SHB_G) == 0 && chi <= 2048) {
+    if (!exact && ctx->use_shb && !ctx->force_warp && t > 32 && t <= 32 + SHB_MAXH && chi >= 32 * SHB_G && chi % (32 * SHB_G) == 0 && chi <= ((size_t)1 << 20)) {
         ctx->shb_plan = shb_make_plan(t, k, ctx->L, ctx->terms_host);
         if (ctx->shb_plan.ok) {
             std::vector<uint64_t> tp(padded, 0);
@@ -1185,7 +1185,7 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
     const int resident_warps = ctx->sm_count * ctx->ctas_per_sm * WARPS_PER_BLOCK;
     // the last quarter of the (popcount-sorted, i.e. cheapest) terms goes out in 32-term items
     // (only when samples are scarce: with plenty of samples the big items balance by themselves)
-    const bool shb = ctx->shb_plan.ok && !a.tri && !ctx->force_warp && (((size_t)a.nterms + 1) & ~(size_t)1) <= 2048;
+    const bool shb = ctx->shb_plan.ok && !a.tri && !ctx->force_warp;       // terms beyond 2048 are read from global memory (L2)
     const int gran = shb ? 32 * SHB_G : 32;                    // items are whole groups of terms
     // k_pairs_shb relabels the sample once per item (about half a batch of work): one item per resident warp is
     // enough there (measured at 2 x 8192 samples: 0.80 ms with 1, 0.92 ms with 8 items per warp)

@@ -737,7 +737,7 @@ def test_level2_binding_reference_host_on_the_c_abi(be, reference):
     assert a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("t,k", [(33, 9), (36, 9), (40, 9), (40, 10), (40, 12), (44, 9), (44, 11)])
+@pytest.mark.parametrize("t,k", [(33, 9), (36, 9), (40, 9), (40, 10), (40, 12), (40, 14), (44, 9), (44, 11), (44, 13)])
 def test_shared_high_block_kernel_equals_generic_kernel(t, k):
     """k_pairs_shb against the generic 64-bit kernel (BG_SHB=0) on the same device-drawn thetas, per-sample values
     bit for bit (both accumulate exact integers), for several random decompositions per (t, k): every width the plan
@@ -757,7 +757,7 @@ def test_shared_high_block_kernel_equals_generic_kernel(t, k):
             L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
             a.set_decomposition(t, False, L)
             b.set_decomposition(t, False, L)
-            th = a.random_states(t, 7 + trial, 0, 0, 192)
+            th = a.random_states(t, 7 + trial, 0, 0, 192 if k < 12 else 48)
             ra = a.sampled_norm_from_states(P, th, project=True)
             rb = b.sampled_norm_from_states(P, th, project=True)
             assert np.array_equal(ra["per_sample"], rb["per_sample"]), (t, k, trial)
