@@ -85,6 +85,7 @@ def load_library():
         "bg_projector_from_bitmatrix": [_P(Projector), i32, i32, _P(C.c_uint8), _P(C.c_uint8), _P(C.c_uint8), _P(C.c_uint8)],
         "bg_sampled_norm": [vp, _P(Projector), u64, i32, u64, dbl, _P(dbl)],
         "bg_exact_norm": [vp, _P(Projector), dbl, _P(dbl)],
+        "bg_exact_norm_parts": [vp, _P(Projector), dbl, _P(dbl)],
         "bg_inner_products": [vp, C.c_size_t, vp, vp, _P(C.c_int32)],
         "bg_sampled_norm_from_states": [vp, _P(Projector), i32, C.c_size_t, vp, _P(C.c_int32), _P(dbl), _P(dbl)],
         "bg_measure_pauli": [vp, C.c_size_t, vp, _P(C.c_int32), _P(u64), _P(u64), _P(dbl)],
@@ -118,7 +119,7 @@ def exported_symbols():
     """Every entry point include/bgnorm.h declares (used by the CPU-side ABI test)."""
     return ["bg_init", "bg_device_count", "bg_shutdown", "bg_last_error", "bg_set_shard", "bg_set_allreduce", "bg_nccl_unique_id", "bg_nccl_join",
             "bg_set_decomposition", "bg_set_decomposition_bitmatrix", "bg_projector_from_bitmatrix",
-            "bg_sampled_norm", "bg_exact_norm", "bg_inner_products", "bg_sampled_norm_from_states",
+            "bg_sampled_norm", "bg_exact_norm", "bg_exact_norm_parts", "bg_inner_products", "bg_sampled_norm_from_states",
             "bg_measure_pauli", "bg_random_states", "bg_decomposition_terms", "bg_get_stats",
             "bg_sampled_prepare", "bg_sampled_run", "bg_sampled_finish", "bg_sampled_norm2", "bg_sampled_prepare2",
             "bg_sampled_finish2", "bg_sampled_per_sample", "bg_set_stream", "bg_measure_int_peak", "bg_decomposition_weights"]

@@ -181,7 +181,10 @@ struct Job {
 // by every probability() call of the front end.
 class Engine {
 public:
-    Engine(int gpus, int device0) : gpus_(gpus), device0_(device0) {}
+    // use_nccl: combine the ranks' partial sums with the in-library NCCL all-reduce (the persistent server: the
+    // communicator is created once) — or, one-shot, on the host: a probability() evaluation has 16 bytes per projector
+    // to combine and creating a communicator for 8 ranks costs ~10 s (measured), a host-side add costs nothing.
+    Engine(int gpus, int device0, bool use_nccl) : gpus_(gpus), device0_(device0), use_nccl_(use_nccl && gpus > 1), parts_(gpus) {}
     ~Engine() { shutdown(); }
 
     // returns "" on success
@@ -194,7 +197,7 @@ public:
             snprintf(buf, sizeof buf, "BG_GPUS=%d from device %d, but %d CUDA device(s) are visible", gpus_, device0_, ndev);
             return buf;
         }
-        if (gpus_ > 1 && bg_nccl_unique_id(nccl_id_)) return std::string("bg_nccl_unique_id: ") + bg_last_error(nullptr);
+        if (use_nccl_ && bg_nccl_unique_id(nccl_id_)) return std::string("bg_nccl_unique_id: ") + bg_last_error(nullptr);
         ready_ = 0;
         for (int r = 0; r < gpus_; r++) th_.emplace_back(&Engine::worker, this, r);
         std::unique_lock<std::mutex> lk(mu_);
@@ -209,6 +212,12 @@ public:
         cv_job_.notify_all();
         cv_done_.wait(lk, [&] { return done_ == gpus_; });
         job_ = nullptr;
+        if (!use_nccl_ && gpus_ > 1 && job->kind == Job::EVALUATE && job->error.empty()) {      // host-side reduction of the ranks' parts
+            double a[4] = {0, 0, 0, 0};
+            for (int r = 0; r < gpus_; r++) for (int j = 0; j < 4; j++) a[j] += parts_[r].v[j];
+            if (job->c.noapprox == 0) { job->numerator = a[0]; job->denominator = a[2]; }
+            else { job->numerator = sqrt(a[0] * a[0] + a[1] * a[1]); job->denominator = sqrt(a[2] * a[2] + a[3] * a[3]); }
+        }
     }
 
     void shutdown() {
@@ -243,7 +252,8 @@ private:
         if (bg_init(&ctx, device0_ + rank)) err = std::string("bg_init: ") + bg_last_error(nullptr);
         else if (bg_set_shard(ctx, rank, gpus_)) err = std::string("bg_set_shard: ") + bg_last_error(ctx);
         const bool all_up = agree(err.empty());
-        if (all_up && gpus_ > 1 && bg_nccl_join(ctx, nccl_id_)) err = std::string("bg_nccl_join: ") + bg_last_error(ctx);
+        if (all_up && use_nccl_ && bg_nccl_join(ctx, nccl_id_)) err = std::string("bg_nccl_join: ") + bg_last_error(ctx);
+        if (all_up && !use_nccl_ && gpus_ > 1 && err.empty() && bg_set_allreduce(ctx, 0)) err = std::string("bg_set_allreduce: ") + bg_last_error(ctx);
         if (!all_up && err.empty()) err = "another GPU of the job failed to initialise";
         unsigned long long seen = 0;
         {
@@ -270,25 +280,41 @@ private:
                 const Config& c = job->c;
                 // everything that can fail on one rank alone (validation, allocation, uploads) comes first ...
                 int rc = jerr.empty() ? bg_set_decomposition(ctx, c.t, c.exact, c.exact ? 0 : c.k, job->L.data()) : 1;
+                // the split-phase job (prepare, then run + finish): both projectors in one launch sequence.  Without a
+                // communicator only bins == 1 is additive over the ranks (a median of partial bin sums is not).
                 const bool split = c.noapprox == 0 && c.bins >= 1 && c.bins <= 4 && job->G.nstabs > 0 && job->H.nstabs > 0 &&
-                                   job->G.nqubits > 0 && job->H.nqubits > 0;
+                                   job->G.nqubits > 0 && job->H.nqubits > 0 && (use_nccl_ || gpus_ == 1 || c.bins == 1);
                 if (!rc && split)
                     rc = bg_sampled_prepare2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
                                              splitmix64(job->seed + 1));
                 if (rc && jerr.empty()) jerr = bg_last_error(ctx);
                 // ... then the ranks agree, and only then run what contains the all-reduce
                 if (agree(jerr.empty())) {
+                    double part[4] = {0, 0, 0, 0};                   // this rank's (numerator re, im, denominator re, im)
                     if (c.noapprox == 0) {            // multiSampledProjector x2 (probability.c:197-198)
                         double out[2] = {0, 0};
                         if (split) { rc = bg_sampled_run(ctx); if (!rc) rc = bg_sampled_finish2(ctx, job->norm, out); }
-                        else rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
-                                                   splitmix64(job->seed + 1), job->norm, out);
+                        else if (use_nccl_ || gpus_ == 1)
+                            rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
+                                                  splitmix64(job->seed + 1), job->norm, out);
+                        else if (rank == 0) {         // closed forms / many bins without a communicator: rank 0 alone, unsharded
+                            rc = bg_set_shard(ctx, 0, 1);
+                            if (!rc) rc = bg_sampled_norm2(ctx, &job->G, &job->H, (uint64_t)c.samples, c.bins, splitmix64(job->seed),
+                                                           splitmix64(job->seed + 1), job->norm, out);
+                            if (bg_set_shard(ctx, 0, gpus_) && !rc) rc = 1;
+                            if (!rc) rc = bg_set_allreduce(ctx, 0);
+                        }
                         num = out[0]; den = out[1];
-                    } else {                          // exactProjector x2 (probability.c:200-201)
+                        part[0] = out[0]; part[2] = out[1];           // without the all-reduce: this rank's share of the mean
+                    } else if (use_nccl_ || gpus_ == 1) {             // exactProjector x2 (probability.c:200-201)
                         rc = bg_exact_norm(ctx, &job->G, job->norm, &num);
                         if (!rc) rc = bg_exact_norm(ctx, &job->H, job->norm, &den);
+                    } else {
+                        rc = bg_exact_norm_parts(ctx, &job->G, job->norm, &part[0]);
+                        if (!rc) rc = bg_exact_norm_parts(ctx, &job->H, job->norm, &part[2]);
                     }
                     if (rc) jerr = bg_last_error(ctx);
+                    for (int j = 0; j < 4; j++) parts_[rank].v[j] = part[j];
                 } else if (jerr.empty()) jerr = "another GPU of the job reported an error";
             }
             {
@@ -302,7 +328,10 @@ private:
         if (ctx) bg_shutdown(ctx);
     }
 
+    struct Part { double v[4] = {0, 0, 0, 0}; };
     int gpus_, device0_;
+    bool use_nccl_;
+    std::vector<Part> parts_;
     uint8_t nccl_id_[128];
     std::vector<std::thread> th_;
     std::mutex mu_;
@@ -448,7 +477,7 @@ static bool write_all(int fd, const char* p, size_t n) {
 // <socket>` keeps the contexts alive; a `bgbackend` started with BG_SERVER=<socket> only forwards its
 // instruction stream and relays the answer, so the drop-in protocol is unchanged.
 static int serve(const char* path, int gpus, int device0, bool chatter) {
-    Engine engine(gpus, device0);
+    Engine engine(gpus, device0, true);
     std::string err = engine.start();
     if (!err.empty()) { fprintf(stderr, "bgbackend --serve: %s\n", err.c_str()); return 1; }
     signal(SIGPIPE, SIG_IGN);                      // a client that goes away before reading its answer must not kill the server
@@ -543,7 +572,8 @@ int main(int argc, char* argv[]) {
     }
     const char* es = getenv("BG_SEED");
     const uint64_t seed = es ? strtoull(es, nullptr, 0) : (uint64_t)getpid();
-    Engine engine(gpus, device0);
+    const char* er = getenv("BG_REDUCE");                  // one-shot: the ranks' parts are added on the host unless BG_REDUCE=nccl
+    Engine engine(gpus, device0, er && strcmp(er, "nccl") == 0);
     process(job, stdout, engine, chatter, seed);
     fflush(stdout);
     engine.shutdown();

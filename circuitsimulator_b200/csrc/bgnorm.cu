@@ -1631,15 +1631,33 @@ extern "C" int bg_sampled_per_sample(bg_ctx* ctx, int projector, uint64_t first,
 }
 
 // ---- exact norm ---------------------------------------------------------------------------
+static int exact_norm_parts(bg_ctx* ctx, const bg_projector* P, double s[2]);
+
 extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, double* out) {
     if (!ctx) return fail(nullptr, "bg_exact_norm: null ctx");
     if (!out) return fail(ctx, "bg_exact_norm: null out");
     if (P && P->nstabs > 0 && P->nqubits == 0) { *out = clifford_closed_form(P); return 0; }
     if (P && P->nstabs == 0) { *out = pow(norm, 2); return 0; }
+    if (ctx->world > 1 && !ctx->allreduce) return fail(ctx, "bg_exact_norm: world > 1 needs the in-library all-reduce (partial |sum| values do not add; bg_exact_norm_parts returns the parts)");
+    double s[2];
+    if (exact_norm_parts(ctx, P, s)) return 1;
+    *out = sqrt(s[0] * s[0] + s[1] * s[1]);                                 // ComplexMag (innerprod.c:198)
+    return 0;
+}
+
+extern "C" int bg_exact_norm_parts(bg_ctx* ctx, const bg_projector* P, double norm, double out[2]) {
+    if (!ctx) return fail(nullptr, "bg_exact_norm_parts: null ctx");
+    if (!out) return fail(ctx, "bg_exact_norm_parts: null out");
+    out[0] = out[1] = 0;
+    const bool mine = ctx->rank == 0 || ctx->allreduce;                     // closed forms: once, not once per rank
+    if (P && P->nstabs > 0 && P->nqubits == 0) { if (mine) out[0] = clifford_closed_form(P); return 0; }
+    if (P && P->nstabs == 0) { if (mine) out[0] = pow(norm, 2); return 0; }
+    return exact_norm_parts(ctx, P, out);
+}
+
+static int exact_norm_parts(bg_ctx* ctx, const bg_projector* P, double s[2]) {
     if (ctx->t <= 0) return fail(ctx, "bg_exact_norm: call bg_set_decomposition first");
-    if (ctx->world > 1 && !ctx->allreduce) return fail(ctx, "bg_exact_norm: world > 1 needs the in-library all-reduce (partial |sum| values do not add)");
     if (check_projector(ctx, P)) return 1;
-    if (P->nstabs == 0) { *out = pow(norm, 2); return 0; }                 // innerprod.c:150
     CK(cudaSetDevice(ctx->device));
     const uint64_t chi = ctx->terms_host.size();
     const uint64_t mine = shard_count(chi, ctx->rank, ctx->world);
@@ -1671,12 +1689,11 @@ extern "C" int bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, do
     }
     CK(cudaEventRecord(EV1(ctx), ctx->stream));
     if (allreduce_red(ctx, 2)) return 1;
-    double s[2] = {0, 0};
-    CK(cudaMemcpyAsync(s, ctx->d_red, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
+    s[0] = s[1] = 0;
+    CK(cudaMemcpyAsync(s, ctx->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes = sizeof s;
+    ctx->stats.d2h_bytes = 2 * sizeof(double);
     if (collect_stats(ctx, 1, false)) return 1;
-    *out = sqrt(s[0] * s[0] + s[1] * s[1]);                                 // ComplexMag (innerprod.c:198)
     return 0;
 }
 

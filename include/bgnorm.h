@@ -127,6 +127,11 @@ int  bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int b
 /* Replaces exactProjector/exactProjectorWork (libcirc/innerprod.c:148-261):
  * | sum_{i<=j} c_ij <P phi_i | phi_j> |, c = 1 on the diagonal, 2 Re off it. */
 int  bg_exact_norm(bg_ctx* ctx, const bg_projector* P, double norm, double* out);
+/* The complex sum before the magnitude is taken (the value a rank sends with sendComplex, innerprod.c:192-195):
+ * out[0] = Re, out[1] = Im of THIS rank's part when the in-library all-reduce is off (bg_set_allreduce(ctx, 0)) — a
+ * host that reduces the ranks itself adds the parts and takes sqrt(re^2 + im^2) — and of the whole sum otherwise.
+ * Closed forms (empty projector, t == 0) are returned in out[0] by rank 0 and as 0 by the other ranks. */
+int  bg_exact_norm_parts(bg_ctx* ctx, const bg_projector* P, double norm, double out[2]);
 
 /* ---- parity / debug entry points --------------------------------------- */
 

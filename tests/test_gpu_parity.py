@@ -692,13 +692,22 @@ def test_multi_gpu_backend_matches_single_gpu():
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     text = _backend_stream("hs_t40_k9_bit0.txt", samples=4096)
     n1, d1, _ = bg.run_backend(text, env=dict(BG_SEED=5, BG_GPUS=1))
-    n2, d2, _ = bg.run_backend(text, env=dict(BG_SEED=5, BG_GPUS=2))
-    assert abs(n2 - n1) <= 1e-13 * abs(n1) and abs(d2 - d1) <= 1e-13 * abs(d1)
-    tof = open(os.path.join(GOLDEN, "streams", "toffoli_111.txt")).read()          # exact-norm path (all-reduce of 2 doubles)
+    tof = open(os.path.join(GOLDEN, "streams", "toffoli_111.txt")).read()          # exact-norm path (2 doubles per projector)
     a1, b1, _ = bg.run_backend(tof, env=dict(BG_SEED=5, BG_GPUS=1))
-    a2, b2, _ = bg.run_backend(tof, env=dict(BG_SEED=5, BG_GPUS=2))
-    assert abs(a2 - a1) <= 1e-12 * abs(a1) and abs(b2 - b1) <= 1e-12 * abs(b1)
-    assert abs(a2 / b2 - 1.0) < 1e-9
+    bins3 = text.split()
+    bins3[4] = "3"                                                                   # median of three bins: not additive over ranks
+    bins3 = "\n".join(bins3) + "\n"
+    m1, e1, _ = bg.run_backend(bins3, env=dict(BG_SEED=5, BG_GPUS=1))
+    # one-shot default: the ranks' parts are added on the host (no communicator per call); BG_REDUCE=nccl: in-library all-reduce
+    for red in ("host", "nccl"):
+        env = dict(BG_SEED=5, BG_GPUS=2, BG_REDUCE=red)
+        n2, d2, _ = bg.run_backend(text, env=env)
+        assert abs(n2 - n1) <= 1e-13 * abs(n1) and abs(d2 - d1) <= 1e-13 * abs(d1), red
+        a2, b2, _ = bg.run_backend(tof, env=env)
+        assert abs(a2 - a1) <= 1e-12 * abs(a1) and abs(b2 - b1) <= 1e-12 * abs(b1), red
+        assert abs(a2 / b2 - 1.0) < 1e-9
+        m2, e2, _ = bg.run_backend(bins3, env=env)
+        assert abs(m2 - m1) <= 1e-13 * abs(m1) and abs(e2 - e1) <= 1e-13 * abs(e1), red
     # more GPUs than the box has: an Error line, not a hang
     with pytest.raises(bg.BGError):
         bg.run_backend(text, env=dict(BG_GPUS=64), timeout=120)
