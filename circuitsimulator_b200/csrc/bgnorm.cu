@@ -34,6 +34,7 @@
 #include "bg_warp_ops.cuh"
 #include "bg_tpp.cuh"
 #include "bg_shb.cuh"
+#include "bg_prep.cuh"
 
 using namespace bg;
 
@@ -212,10 +213,91 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
     }
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------
+// k_prepare_tps — the hot path's k_prepare: one THREAD per sample (bg_prep.cuh)
+// ------------------------------------------------------------------------------------------
+// Device-drawn theta, projected: what a sampled probability() job needs.  (k_prepare stays for host-supplied states,
+// decomposition terms, unprojected samples, the raw-state dump, and under BG_PREP=warp.)
+// Shared memory: 2 * nr rows (J, then the parity checks; nr = t rounded up to 8) of BG_PREP_THREADS + 1 words: a
+// thread walks its column, consecutive lanes in consecutive banks; the odd row length makes the transposed read
+// of the write-out (lanes across rows, one sample at a time: coalesced 256-byte stores) at most two-way conflicted.
+#ifndef BG_PREP_THREADS
+#define BG_PREP_THREADS 64
+#endif
+template <typename W> static size_t prep_tps_smem(int t) {
+    return (size_t)2 * ((t + 7) & ~7) * (BG_PREP_THREADS + 1) * sizeof(W);
+}
+template <typename W>
+__global__ void __launch_bounds__(BG_PREP_THREADS) k_prepare_tps(PrepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NS = (int)(sizeof(W) / 4);
+    constexpr uint32_t RS = (BG_PREP_THREADS + 1) * (uint32_t)sizeof(W);
+    const int lane = bg_lane(), wib = (int)(threadIdx.x >> 5);
+    const int n = a.t, nr = (n + 7) & ~7;
+    Rows<W> J, C;
+    J.base = nullptr; J.stride = 0; C.base = nullptr; C.stride = 0;
+    J.sbase = smem_u32(smem_raw) + threadIdx.x * (uint32_t)sizeof(W); J.sstride = RS;
+    C.sbase = J.sbase + (uint32_t)nr * RS; C.sstride = RS;
+    const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)(wib * 32) * (uint32_t)sizeof(W);
+    const int warps = (int)gridDim.x * (BG_PREP_THREADS / 32), gw = (int)blockIdx.x * (BG_PREP_THREADS / 32) + wib;
+    const int ngroups = (a.n_samples + 31) >> 5;
+    for (int g = gw; g < ngroups; g += warps) {
+        const int idx = g * 32 + lane;
+        TSample<W> s;
+        s.Cpend = 0;
+        int route = ROUTE_DEAD;
+        if (idx < a.n_samples) {
+            const bool second = idx >= a.n_first;
+            t_random_ambient<W>(J, C, n, second ? a.seed2 : a.seed, a.bin,
+                                a.first + (uint64_t)(second ? idx - a.n_first : idx) * a.stride, a.cdf, s);
+            t_project<W>(J, C, n, s, second ? a.P2 : a.P);
+            if (a.zw) { longlong2* z = reinterpret_cast<longlong2*>(a.zw + (size_t)idx * 4); z[0] = z[1] = make_longlong2(0, 0); }
+            if (a.zw2) { longlong2* z = reinterpret_cast<longlong2*>(a.zw2 + (size_t)idx * 4); z[0] = z[1] = make_longlong2(0, 0); }
+            SampleRec* r = &a.recs[idx];
+            if (s.alive) {
+                const int nchk = tpopc(s.Cpend);
+                route = a.force_warp ? ROUTE_WARP
+                        : a.shb ? (nchk > SHB_MAXLAM ? ROUTE_TPP_MANY : ROUTE_SHB)
+                                : (nchk > TPP_MAXC ? ROUTE_TPP_MANY : ROUTE_TPP);
+                if (route != ROUTE_TPP && route != ROUTE_SHB) atomicAdd(a.n_warp_routed, 1ull);
+                *reinterpret_cast<int4*>(&r->alive) = make_int4(route, n - nchk, s.npf, (int)s.Q);
+                ulonglong2* q = reinterpret_cast<ulonglong2*>(&r->D1);
+                q[0] = make_ulonglong2((uint64_t)s.D1, (uint64_t)s.D2);
+                q[1] = make_ulonglong2((uint64_t)s.Cpend, (uint64_t)s.Cbeta);
+            } else {
+                *reinterpret_cast<int4*>(&r->alive) = make_int4(0, 0, 0, 0);
+            }
+        }
+        __syncwarp();
+        for (int j = 0; j < 32; j++) {
+            const int sidx = g * 32 + j;
+            if (sidx >= a.n_samples) break;
+            const int rt = __shfl_sync(BG_FULL, route, j);
+            const W cp = shflw(s.Cpend, j);
+            if (rt == ROUTE_DEAD) continue;
+            SampleRec* r = &a.recs[sidx];
+#pragma unroll
+            for (int hh = 0; hh < NS; hh++) {
+                const int v = lane + 32 * hh;
+                W jv = 0, cv = 0;
+                if (v < n) {
+                    const uint32_t ad = wbase + (uint32_t)j * (uint32_t)sizeof(W) + (uint32_t)v * RS;
+                    t_lds(ad, jv);
+                    if ((cp >> v) & 1) t_lds(ad + (uint32_t)nr * RS, cv);
+                }
+                r->J[v] = (uint64_t)jv;
+                r->Cw[v] = (uint64_t)cv;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_pairs
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Stage `bytes` (multiple of 16, 16-byte aligned on both sides) from global to shared memory
 // with the TMA bulk-copy engine; completion is signalled on an mbarrier.  SASS: UBLKCP.
@@ -754,6 +836,8 @@ struct bg_ctx {
 #endif                          // BG_LAM_MAX: parity checks carried as Lagrange variables (0: pivot every check per term)
     const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
+    int prep_warp = 0;              // BG_PREP=warp: draw + project the samples with the warp-per-sample k_prepare
+    int prep_ctas_per_sm[2][BG_MAX_T + 1] = {};   // k_prepare_tps: resident CTAs per SM by (word size, t), 0 = not asked yet
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
@@ -888,6 +972,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e7 = getenv("BG_FUSE2")) ctx->fuse2 = atoi(e7) != 0;
     if (const char* e8 = getenv("BG_SHB")) ctx->use_shb = atoi(e8) != 0;
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
+    if (const char* e9 = getenv("BG_PREP")) ctx->prep_warp = strcmp(e9, "warp") == 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) { ctx->items_factor = v; ctx->items_factor_set = true; } }
     *out = ctx;
     return 0;
@@ -1138,6 +1223,22 @@ template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepA
     ctx->stats.launches++;
     return 0;
 }
+// k_prepare_tps: as many CTAs as are resident at once (occupancy x SMs), at most one warp per group of 32 samples
+template <typename W> static int launch_prepare_tps(bg_ctx* ctx, const PrepArgs& a) {
+    const size_t smem = prep_tps_smem<W>(a.t);
+    int& per_sm = ctx->prep_ctas_per_sm[sizeof(W) == 8][a.t];
+    if (per_sm == 0) {
+        CK(cudaFuncSetAttribute(k_prepare_tps<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prepare_tps<W>, BG_PREP_THREADS, smem));
+        if (per_sm < 1) return fail(ctx, "k_prepare_tps does not fit an SM at t = %d", a.t);
+    }
+    const int groups = (a.n_samples + 31) / 32, wpb = BG_PREP_THREADS / 32;
+    const int blocks = std::max(1, std::min((groups + wpb - 1) / wpb, ctx->sm_count * per_sm));
+    k_prepare_tps<W><<<blocks, BG_PREP_THREADS, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
 static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     if (a.n_samples <= 0) return 0;
     CK(cudaMemsetAsync(CNT(ctx) + 4 * ctx->cur, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -1145,6 +1246,8 @@ static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     a.shb = (ctx->shb_plan.ok && src != SRC_TERMS) ? 1 : 0;     // SRC_TERMS = the exact-norm path (tri mode): generic kernels
     if (!a.P2) a.n_first = a.n_samples;
     a.n_warp_routed = CNT(ctx) + 4 * ctx->cur + 2;
+    if (src == SRC_RNG && a.project && !a.raw_out && !ctx->prep_warp)
+        return a.t <= 32 ? launch_prepare_tps<uint32_t>(ctx, a) : launch_prepare_tps<uint64_t>(ctx, a);
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
 

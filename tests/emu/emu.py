@@ -57,7 +57,18 @@ class Emu:
         lib.emu_chi_seconds.argtypes = [C.c_int]
         lib.emu_chi_seconds.restype = C.c_double
         lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
+        lib.emu_prepare_both.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(Projector),
+                                         _P(C.c_uint64), _P(C.c_uint64)]
         self.lib = lib
+
+    def prepare_both(self, n, seed, bin_, sample, cdf, P):
+        """One device-RNG sample projected by P: the SampleRec fields (136 uint64) as the warp-per-sample code and
+        as the thread-per-sample code (bg_prep.cuh) produce them."""
+        a = (C.c_uint64 * 136)()
+        b = (C.c_uint64 * 136)()
+        arr = (C.c_double * len(cdf))(*cdf)
+        self.lib.emu_prepare_both(n, seed, bin_, sample, arr, C.byref(P), a, b)
+        return list(a), list(b)
 
     def inner_product(self, a, b):
         out = (C.c_int32 * 3)()

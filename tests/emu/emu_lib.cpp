@@ -8,6 +8,7 @@
 #include "bg_warp_ops.cuh"
 #include "bg_tpp.cuh"
 #include "bg_shb.cuh"
+#include "bg_prep.cuh"
 #include <string.h>
 #include <algorithm>
 #include <chrono>
@@ -192,6 +193,47 @@ template <typename W> static int expsum_selftest(uint64_t seed, int trials) {
     return bad;
 }
 
+// One sample of the device RNG, projected by P, through BOTH formulations of k_prepare: the warp-per-sample code
+// (native_random + make_ambient + project_ambient under the warp emulator) and the thread-per-sample code
+// (bg_prep.cuh).  rec = [alive, k1, npf, Q, D1, D2, Cpend, Cbeta, J[64], Cw[64]] as uint64 (the fields of SampleRec).
+template <int NS>
+static void prepare_both(int n, uint64_t seed, uint32_t bin, uint64_t sample, const double* cdf, const bg_projector* P,
+                         uint64_t* rec_warp, uint64_t* rec_thread) {
+    typedef typename WordOf<NS>::T W;
+    memset(rec_warp, 0, 136 * sizeof(uint64_t));
+    memset(rec_thread, 0, 136 * sizeof(uint64_t));
+    emu::run([&]() {
+        Native<NS> st; Ambient<NS> am;
+        native_random<NS>(st, n, seed, bin, sample, cdf);
+        make_ambient<NS>(st, am);
+        int npf = 0;
+        const bool ok = project_ambient<NS>(am, P, npf);
+        const int lane = bg_lane();
+        if (lane == 0) rec_warp[0] = ok;
+        if (!ok) return;
+        if (lane == 0) {
+            rec_warp[1] = (uint64_t)am.k1; rec_warp[2] = (uint64_t)npf; rec_warp[3] = am.f.Q;
+            rec_warp[4] = am.f.D1; rec_warp[5] = am.f.D2; rec_warp[6] = am.Cpend; rec_warp[7] = am.Cbeta;
+        }
+        for (int s = 0; s < NS; s++) { rec_warp[8 + lane + 32 * s] = am.f.J[s]; rec_warp[72 + lane + 32 * s] = am.Cw[s]; }
+    });
+    W jr[64], cr[64];
+    for (int i = 0; i < 64; i++) { jr[i] = (W)0xdeadbeefdeadbeefull; cr[i] = (W)0xfeedfacefeedfaceull; }   // stale shared memory
+    Rows<W> J, C;
+    J.base = jr; J.stride = 1; J.sbase = 0; J.sstride = 0;
+    C.base = cr; C.stride = 1; C.sbase = 0; C.sstride = 0;
+    TSample<W> s;
+    t_random_ambient<W>(J, C, n, seed, bin, sample, cdf, s);
+    t_project<W>(J, C, n, s, P);
+    rec_thread[0] = s.alive;
+    if (!s.alive) return;
+    rec_thread[1] = (uint64_t)(n - tpopc(s.Cpend)); rec_thread[2] = (uint64_t)s.npf; rec_thread[3] = s.Q;
+    rec_thread[4] = s.D1; rec_thread[5] = s.D2; rec_thread[6] = s.Cpend; rec_thread[7] = s.Cbeta;
+    for (int v = 0; v < n; v++) {
+        rec_thread[8 + v] = jr[v];
+        rec_thread[72 + v] = ((s.Cpend >> v) & 1) ? cr[v] : 0;
+    }
+}
 extern "C" {
 
 // <b|a> through the generic path
@@ -337,6 +379,12 @@ void emu_random_state(int n, uint64_t seed, uint32_t bin, uint64_t sample, const
         if (n <= 32) warp_random_state<1>(n, seed, bin, sample, cdf, out, A);
         else warp_random_state<2>(n, seed, bin, sample, cdf, out, A);
     });
+}
+
+void emu_prepare_both(int n, uint64_t seed, uint32_t bin, uint64_t sample, const double* cdf, const bg_projector* P,
+                      uint64_t* rec_warp, uint64_t* rec_thread) {
+    if (n <= 32) prepare_both<1>(n, seed, bin, sample, cdf, P, rec_warp, rec_thread);
+    else prepare_both<2>(n, seed, bin, sample, cdf, P, rec_warp, rec_thread);
 }
 
 }  // extern "C"

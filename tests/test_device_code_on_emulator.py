@@ -223,3 +223,69 @@ def test_exponential_sums_by_enumeration(variant, wordbits):
     from emu.emu import Emu
     emu = Emu(variant)
     assert emu.lib.emu_expsum_selftest(wordbits, 7, 20000) == 0
+
+
+def _random_projector(rs, t, ns, kind):
+    """kind 0: arbitrary Paulis (light and dense X parts); kind 1: commuting Z-type generators with real phases, some
+    repeated or negated — these add parity checks (measurePauli's shrink branch), leave the state alone, or kill it."""
+    from oracle.oracle import Projector
+    mask = (1 << t) - 1
+    ph, xs, zs = [], [], []
+    for _ in range(ns):
+        if kind == 1:
+            if zs and rs.randint(0, 6) == 0:
+                j = int(rs.randint(0, len(zs)))
+                xs.append(0); zs.append(zs[j]); ph.append(ph[j] if rs.randint(0, 8) else ph[j] ^ 2)
+            else:
+                z = int(rs.randint(0, 2 ** 62)) & mask
+                if rs.randint(0, 2):
+                    z &= int(rs.randint(0, 2 ** 62)) & int(rs.randint(0, 2 ** 62))
+                xs.append(0); zs.append(z); ph.append(2 * int(rs.randint(0, 2)))
+            continue
+        ph.append(int(rs.randint(0, 4)))
+        if rs.randint(0, 4):
+            x = 0
+            for q in rs.choice(t, size=min(t, int(rs.randint(0, 4))), replace=False):
+                x |= 1 << int(q)
+        else:
+            x = int(rs.randint(0, 2 ** 62)) & mask
+        xs.append(x)
+        zs.append(int(rs.randint(0, 2 ** 62)) & mask)
+    return Projector.make(t, ph, xs, zs)
+
+
+@pytest.mark.parametrize("stream,ns", [("htstack_t4.txt", 64), ("hs_t16_bit6.txt", 48), ("hs_t40_k9_bit0.txt", 48),
+                                       ("phase_estimation_q0.txt", 48), ("toffoli_q0.txt", 32)])
+def test_thread_per_sample_prepare_equals_warp_per_sample(emu, oracle, stream, ns):
+    """bg_prep.cuh (k_prepare_tps: one thread per sample) against the warp-per-sample code it replaces on the
+    hot path: every field of the sample record, for the projectors of the golden streams."""
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", stream))
+    t = cfg["t"]
+    cdf = oracle.dimension_cdf(t)
+    dead = 0
+    for pi, P in enumerate((G, H)):
+        for s in range(ns):
+            a, b = emu.prepare_both(t, 77 + pi, 1, s, cdf, P)
+            assert a == b, (stream, pi, s, [i for i in range(136) if a[i] != b[i]][:8])
+            dead += a[0] == 0
+    assert dead < 2 * ns
+
+
+@pytest.mark.parametrize("t", [1, 2, 5, 8, 17, 31, 32, 33, 40, 47, 63, 64])
+def test_thread_per_sample_prepare_random_projectors(emu, oracle, t):
+    """Random generators at every word-size boundary: arbitrary Paulis (the extend and the phase branch of
+    measurePauli) and commuting Z-type sets with repeats (new parity checks up to dimension 0, unchanged states,
+    annihilated samples)."""
+    rs = np.random.RandomState(100 + t)
+    cdf = oracle.dimension_cdf(t)
+    seen_dead = seen_checks = 0
+    for trial in range(16):
+        kind = trial & 1
+        P = _random_projector(rs, t, int(rs.randint(0, (t if kind else 2 * t) + 1)), kind)
+        for s in range(5):
+            a, b = emu.prepare_both(t, 5 + trial, 2, 1000 * trial + s, cdf, P)
+            assert a == b, (t, trial, s, [i for i in range(136) if a[i] != b[i]][:8])
+            seen_dead += a[0] == 0
+            seen_checks += bin(a[6]).count("1") > 3
+    if t >= 8:
+        assert seen_checks > 0 and seen_dead > 0

@@ -778,6 +778,56 @@ def test_shared_high_block_kernel_equals_generic_kernel(t, k):
         b.close()
 
 
+@pytest.mark.parametrize("stream,k,exact", [("hs_t40_k9_bit0.txt", 6, False), ("hs_t16_bit6.txt", 0, True),
+                                            ("htstack_t4.txt", 0, True), ("phase_estimation_q0.txt", 5, False),
+                                            ("random_t33", 5, False), ("random_t64", 4, False), ("random_t32", 4, False),
+                                            ("zchecks_t40", 6, False)])
+def test_thread_per_sample_prepare_equals_warp_per_sample(stream, k, exact):
+    """k_prepare_tps (one thread per sample, bg_prep.cuh — the hot path's draw + projection) against the
+    warp-per-sample k_prepare (BG_PREP=warp) on the device: the same seeds give the same per-sample values bit for bit
+    (exact integer sums), for a sample count that is not a multiple of 32, both projectors of a fused job, 32- and
+    64-bit words, projectors that annihilate samples and projectors that leave many parity checks."""
+    import circuitsimulator_b200 as bg
+    a = bg.Backend(0)
+    os.environ["BG_PREP"] = "warp"
+    try:
+        b = bg.Backend(0)
+    finally:
+        del os.environ["BG_PREP"]
+    try:
+        if stream.startswith("random_t") or stream.startswith("zchecks_t"):
+            t = int(stream.split("_t")[1])
+            rs = np.random.RandomState(t)
+            if stream.startswith("zchecks"):       # commuting Z-type generators: a new parity check per generator, some kill
+                zs = [int(rs.randint(0, 2 ** 62)) & int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(9)]
+                G = bg.Projector.make(t, [0, 2, 0, 2, 0, 0, 2, 0, 0], [0] * 9, zs)
+                H = bg.Projector.make(t, [0, 2, 0, 2, 0, 0, 2, 0, 2, 0], [0] * 10, zs + [zs[0] ^ zs[3]])
+            else:
+                G, _ = _random_projector(rs, t, 2 * t)
+                H, _ = _random_projector(rs, t, 7)
+        else:
+            cfg, Gp, Hp = parse_stream(os.path.join(GOLDEN, "streams", stream))
+            t = cfg["t"]
+            G, H = to_bg(Gp), to_bg(Hp)
+        L = [] if exact else _bench_L(k, t)
+        samples = 1000 + 13
+        dead = 0
+        for be in (a, b):
+            be.set_decomposition(t, exact, L)
+        ra = a.sampled_norm2(G, H, samples, 1, 11, 12, 1.0)
+        rb = b.sampled_norm2(G, H, samples, 1, 11, 12, 1.0)
+        assert ra == rb
+        for pj in (0, 1):
+            pa, pb = a.sampled_per_sample(pj, 0, samples), b.sampled_per_sample(pj, 0, samples)
+            assert np.array_equal(pa, pb), (stream, pj, int(np.argmax(pa != pb)))
+            dead += int((pa == 0).sum())
+        assert a.sampled_norm(G, 77, 1, 5, 1.0) == b.sampled_norm(G, 77, 1, 5, 1.0)          # one projector, < 3 warps
+        assert dead < 2 * samples
+    finally:
+        a.close()
+        b.close()
+
+
 def test_phase_estimation_chain_approaches_the_exact_distribution():
     """BASELINE config 5 end to end: the probability() calls sampleQubits makes on circuits/phaseEstimation.circ
     (one per sampled qubit, conditioned on the outcomes before it: libcirc/sample.py:32-83), written by the unmodified
