@@ -849,7 +849,9 @@ struct bg_ctx {
     uint64_t samples = 0; int bins = 1; uint64_t seeds[2] = {0, 0};
     bool prepared = false;
     bool per_valid = false;         // d_per holds the per-sample values of a finished job
-    bg_projector* h_stage = nullptr; cudaEvent_t ev_stage = nullptr;   // pinned staging copy of the projectors + its upload event
+    // pinned staging copies of the projectors + their upload events: two sets, used in turn, so that the projectors of
+    // the next job can be staged while the previous job (and its upload) is still in flight
+    bg_projector* h_stage = nullptr; cudaEvent_t ev_stage[2] = {nullptr, nullptr}; unsigned stage_seq = 0;
     bg_projector h_P[2];            // what d_P holds (a repeated prepare with the same content keeps the captured graph)
     bool phase_events = false;
     int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
@@ -954,8 +956,9 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (cudaMalloc((void**)&ctx->d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void**)&ctx->h_stage, 2 * sizeof(bg_projector), cudaHostAllocDefault) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_stage, 4 * sizeof(bg_projector), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_red, 16 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_partials, 64 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_ticket, 2 * sizeof(unsigned int)) != cudaSuccess ||
@@ -995,7 +998,7 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
     if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    for (int j = 0; j < 2; j++) if (ctx->ev_stage[j]) cudaEventDestroy(ctx->ev_stage[j]);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1416,26 +1419,29 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     if (bins < 1) return fail(ctx, "bg_sampled_prepare: bins = %d", bins);
     if (samples < 1) return fail(ctx, "bg_sampled_prepare: samples = 0");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->run_seq != ctx->fin_seq) {            // an unfinished job of the previous configuration
-        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->cstream));
-        ctx->fin_seq = ctx->run_seq;
-    }
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
     // the projectors go through a pinned staging copy, asynchronously on the job's stream (the kernels read d_P when
     // they run, so a captured graph stays valid); a job of the same shape and seeds keeps its graph
     bool same_shape = ctx->prepared && ctx->nproj == nproj && ctx->samples == samples && ctx->bins == bins;
     for (int j = 0; same_shape && j < nproj; j++) same_shape = ctx->seeds[j] == seeds[j];
+    if (!same_shape && ctx->run_seq != ctx->fin_seq) {   // an unfinished job of another shape: its buffers are about to change
+        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->cstream));
+        ctx->fin_seq = ctx->run_seq;
+    }
     if (!same_shape && ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
     bool same_P = same_shape;
     for (int j = 0; same_P && j < nproj; j++) same_P = memcmp(&ctx->h_P[j], Ps[j], sizeof(bg_projector)) == 0;
     ctx->stats.h2d_bytes = 0;
     if (!same_P) {
-        if (ctx->run_seq != ctx->fin_seq) return fail(ctx, "bg_sampled_prepare: a job is still in flight");
-        CK(cudaEventSynchronize(ctx->ev_stage));         // the previous upload has left the staging buffer
-        for (int j = 0; j < nproj; j++) ctx->h_stage[j] = *Ps[j];
-        CK(cudaMemcpyAsync(ctx->d_P, ctx->h_stage, (size_t)nproj * sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
+        // New projectors for a job of the same shape may be staged while the previous job is still in flight: the
+        // upload is ordered on the job's stream behind that job's kernels, and the staging sets alternate.
+        const unsigned ss = ctx->stage_seq++ & 1u;
+        CK(cudaEventSynchronize(ctx->ev_stage[ss]));     // the upload before last has left this staging set
+        bg_projector* hs = ctx->h_stage + 2 * ss;
+        for (int j = 0; j < nproj; j++) hs[j] = *Ps[j];
+        CK(cudaMemcpyAsync(ctx->d_P, hs, (size_t)nproj * sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_stage[ss], ctx->stream));
         ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
     }
     ctx->nproj = nproj; ctx->samples = samples; ctx->bins = bins;

@@ -417,6 +417,36 @@ def test_pipelined_runs_two_in_flight(be):
         be.sampled_finish2(1.0)               # nothing in flight
 
 
+def test_new_projectors_staged_while_a_job_is_in_flight(be):
+    """The end-to-end pipeline bench.py times: bg_sampled_prepare2 with NEW projector bytes while the previous job of
+    the same shape has not been collected (staging sets alternate, the upload is ordered behind the running job on
+    its stream).  Each job must return what the same projectors give one call at a time."""
+    import circuitsimulator_b200 as bg
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
+    be.set_decomposition(cfg["t"], True)
+    g = to_bg(G)                 # (the stream's own H' projects onto the same space as G': the hidden shift is deterministic)
+    h, _ = _random_projector(np.random.RandomState(4), cfg["t"], 5)
+    pairs = [(g, h), (h, g), (g, g), (h, h), (g, h)]
+    want = [be.sampled_norm2(a, b, 5000, 1, 7, 8, 1.0) for a, b in pairs]
+    assert len(set(want)) == len(want) - 1
+    got = []
+    be.sampled_prepare2(*pairs[0], 5000, 1, 7, 8)
+    be.sampled_run()
+    for a, b in pairs[1:]:
+        be.sampled_prepare2(a, b, 5000, 1, 7, 8)        # previous job still in flight
+        be.sampled_run()
+        got.append(be.sampled_finish2(1.0))
+    got.append(be.sampled_finish2(1.0))
+    assert got == want
+    # a job of another shape drops what is in flight (its buffers change) instead of returning stale numbers
+    be.sampled_run()
+    be.sampled_prepare2(g, h, 1234, 1, 7, 8)
+    with pytest.raises(bg.BGError):
+        be.sampled_finish2(1.0)
+    be.sampled_run()
+    assert be.sampled_finish2(1.0) == be.sampled_norm2(g, h, 1234, 1, 7, 8, 1.0)
+
+
 def test_persistent_server_mode(tmp_path):
     """`bgbackend --serve <socket>` keeps the CUDA contexts alive across probability() calls; a client
     started with BG_SERVER=<socket> relays the same protocol."""
