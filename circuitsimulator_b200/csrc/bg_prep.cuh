@@ -191,27 +191,36 @@ BG_HD void t_random_ambient(const Rows<W>& J, const Rows<W>& C, int n, uint64_t 
     o.npf = 0; o.alive = true;
 }
 
+// f(q, bit q as a word) for every set bit of m, from the top: 64-bit masks are walked as two 32-bit words (one FLO
+// and one xor per bit; the 64-bit "lowest bit, clear it" idiom costs a dozen instructions)
+template <typename F> BG_HD void t_each_bit(uint32_t m, F f) {
+    while (m) { const int c = thighest(m); const uint32_t b = 1u << c; m ^= b; f(c, b); }
+}
+template <typename F> BG_HD void t_each_bit(uint64_t m, F f) {
+    uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+    while (hi) { const int c = thighest(hi); const uint32_t b = 1u << c; hi ^= b; f(c + 32, (uint64_t)b << 32); }
+    while (lo) { const int c = thighest(lo); const uint32_t b = 1u << c; lo ^= b; f(c, (uint64_t)b); }
+}
+
 // ---- one generator i^m Z(zeta) X(xi) of the projector on a sample in ambient form: ambient_measure
 // (bg_device.cuh) per thread, same case analysis, same choices (the dropped check is the one in the lowest
 // hit slot, a new check goes to the slot of its lowest bit).  Returns 0 (annihilated), 1, or 2 (factor 2^-1/2).
 template <typename W>
 BG_HD int t_ambient_measure(const Rows<W>& J, const Rows<W>& C, int n, int nr, TSample<W>& s, uint32_t m, W zeta, W xi) {
     const W maskn = tlowmask<W>(n);
-    // eta = zeta + J xi (J symmetric: the xor of the rows in xi), tri = sum_{q<r in xi} J_qr
-    W eta = zeta;
-    uint32_t tri = 0;
-    for (W rem = xi; rem; rem &= rem - 1) {
-        const int q = tlowest(rem);
+    // eta = zeta + J xi (J symmetric: the xor of the rows in xi); tri = sum_{q<r in xi} J_qr = the parity of
+    // sum_q |J_q & (the bits of xi visited before q)|, every unordered pair once
+    W eta = zeta, acc = 0, seen = 0;
+    t_each_bit(xi, [&](int q, W b) {
         const W row = J.get(q);
         eta ^= row;
-        tri ^= tpar<W>(row & xi & tlowmask<W>(q));
-    }
+        acc ^= row & seen;
+        seen |= b;
+    });
+    const uint32_t tri = tpar<W>(acc);
     eta &= maskn;
     W hit = 0;
-    for (W rem = s.Cpend; rem; rem &= rem - 1) {
-        const int j = tlowest(rem);
-        if (tpar<W>(C.get(j) & xi)) hit |= tbit<W>(j);
-    }
+    t_each_bit(s.Cpend, [&](int j, W b) { hit |= b & tfill<W>(tpar<W>(C.get(j) & xi)); });
     const uint32_t w0 = (2u * m + 2u * (uint32_t)tpopc(s.D1 & xi) + 4u * (uint32_t)tpopc(s.D2 & xi) + 4u * tri) & 7u;
     W X = 0, Y = 0, Z = 0, U = 0;
     int ret = 2;
@@ -220,8 +229,8 @@ BG_HD int t_ambient_measure(const Rows<W>& J, const Rows<W>& C, int n, int nr, T
         const int p0 = tlowest(hit);
         const W bp0 = tbit<W>(p0);
         const W c0 = C.get(p0);
-        const uint32_t b0 = tget<W>(s.Cbeta, p0);
-        for (W rem = hit & ~bp0; rem; rem &= rem - 1) { const int v = tlowest(rem); C.put(v, C.get(v) ^ c0); }
+        const bool b0 = (s.Cbeta & bp0) != 0;
+        t_each_bit(hit ^ bp0, [&](int v, W) { C.put(v, C.get(v) ^ c0); });
         if (b0) s.Cbeta ^= hit;
         s.Cbeta &= ~bp0; s.Cpend &= ~bp0;
         s.D2 ^= (c0 & eta) ^ (b0 ? eta : (W)0);
@@ -236,20 +245,20 @@ BG_HD int t_ambient_measure(const Rows<W>& J, const Rows<W>& C, int n, int nr, T
         }
     } else if (w0 == 0u || w0 == 4u) {
         // projector onto eta.y = w0/4 inside K
-        W er = eta;
-        uint32_t br = w0 >> 2;
-        for (W f = eta & s.Cpend; f; f &= f - 1) { const int q = tlowest(f); er ^= C.get(q); br ^= tget<W>(s.Cbeta, q); }
+        W er = eta, brm = 0;
+        t_each_bit(eta & s.Cpend, [&](int q, W b) { er ^= C.get(q); brm ^= b; });
+        const uint32_t br = (w0 >> 2) ^ tpar<W>(brm & s.Cbeta);
         if (er == 0) ret = br ? 0 : 1;
         else {
             const int p = tlowest(er);
-            for (W f = s.Cpend; f; f &= f - 1) {
-                const int q = tlowest(f);
+            const W bp = tbit<W>(p), brw = tfill<W>(br);
+            t_each_bit(s.Cpend, [&](int q, W b) {
                 const W c = C.get(q);
-                if ((c >> p) & 1) { C.put(q, c ^ er); s.Cbeta ^= (W)br << q; }
-            }
+                if (c & bp) { C.put(q, c ^ er); s.Cbeta ^= b & brw; }
+            });
             C.put(p, er);
-            s.Cpend |= tbit<W>(p);
-            s.Cbeta = (s.Cbeta & ~tbit<W>(p)) | ((W)br << p);
+            s.Cpend |= bp;
+            s.Cbeta = (s.Cbeta & ~bp) | (bp & brw);
         }
     } else {
         // w0 in {2,6}: 1 + w^{w(y)} = sqrt2 w^{+-1}
