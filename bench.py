@@ -768,7 +768,10 @@ def main():
                 "traffic": None,
                 "hbm_gbs_peak": peaks.get("hbm_gbs"),
                 # NOT measured in this run: constants read from the committed ncu capture of the same kernel at N=1
-                "from_profiles": wm.get("from_profiles")}
+                "from_profiles": wm.get("from_profiles"),
+                # overlap mode (few samples per GPU: the draw + projection kernel of step i+1 runs beside the pair kernel
+                # of step i on a second stream): kernel_ms / prepare_ms are then event intervals of kernels that share the GPU
+                "overlap_mode": bool(ctx.stats().get("overlapped", 0))}
         fp = wm.get("from_profiles") or {}
         if fp.get("dram_bytes_per_launch") and fp.get("pairs_per_launch_ncu"):
             roof["traffic"] = fp["dram_bytes_per_launch"] * per_launch_pairs / fp["pairs_per_launch_ncu"]

@@ -56,7 +56,7 @@ class Projector(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("pairs", C.c_uint64), ("pair_launches", C.c_uint64),
                 ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("prepare_ms", C.c_double), ("pairs_ms", C.c_double)]
+                ("prepare_ms", C.c_double), ("pairs_ms", C.c_double), ("overlapped", C.c_uint64)]
 
 
 _lib = None

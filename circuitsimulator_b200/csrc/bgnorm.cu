@@ -220,20 +220,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // ------------------------------------------------------------------------------------------
 // Device-drawn theta, projected: what a sampled probability() job needs.  (k_prepare stays for host-supplied states,
 // decomposition terms, unprojected samples, the raw-state dump, and under BG_PREP=warp.)
-// Shared memory: 2 * nr rows (J, then the parity checks; nr = t rounded up to 8) of BG_PREP_THREADS + 1 words: a
+// Shared memory: 2 * nr rows (J, then the parity checks; nr = t rounded up to 8) of THREADS + 1 words: a
 // thread walks its column, consecutive lanes in consecutive banks; the odd row length makes the transposed read
 // of the write-out (lanes across rows, one sample at a time: coalesced 256-byte stores) at most two-way conflicted.
-#ifndef BG_PREP_THREADS
-#define BG_PREP_THREADS 64
-#endif
-template <typename W> static size_t prep_tps_smem(int t) {
-    return (size_t)2 * ((t + 7) & ~7) * (BG_PREP_THREADS + 1) * sizeof(W);
+// CTAs of 64 threads by default; of 32 in overlap mode (bg_ctx::overlap), where one such CTA — 2048 registers, 21 KB of
+// shared memory at t = 40 — fits an SM beside the ten resident CTAs of k_pairs_shb.
+template <typename W, int THREADS> static size_t prep_tps_smem(int t) {
+    return (size_t)2 * ((t + 7) & ~7) * (THREADS + 1) * sizeof(W);
 }
-template <typename W>
-__global__ void __launch_bounds__(BG_PREP_THREADS) k_prepare_tps(PrepArgs a) {
+template <typename W, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_prepare_tps(PrepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NS = (int)(sizeof(W) / 4);
-    constexpr uint32_t RS = (BG_PREP_THREADS + 1) * (uint32_t)sizeof(W);
+    constexpr uint32_t RS = (THREADS + 1) * (uint32_t)sizeof(W);
     const int lane = bg_lane(), wib = (int)(threadIdx.x >> 5);
     const int n = a.t, nr = (n + 7) & ~7;
     Rows<W> J, C;
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(BG_PREP_THREADS) k_prepare_tps(PrepArgs a) {
     J.sbase = smem_u32(smem_raw) + threadIdx.x * (uint32_t)sizeof(W); J.sstride = RS;
     C.sbase = J.sbase + (uint32_t)nr * RS; C.sstride = RS;
     const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)(wib * 32) * (uint32_t)sizeof(W);
-    const int warps = (int)gridDim.x * (BG_PREP_THREADS / 32), gw = (int)blockIdx.x * (BG_PREP_THREADS / 32) + wib;
+    const int warps = (int)gridDim.x * (THREADS / 32), gw = (int)blockIdx.x * (THREADS / 32) + wib;
     const int ngroups = (a.n_samples + 31) >> 5;
     for (int g = gw; g < ngroups; g += warps) {
         const int idx = g * 32 + lane;
@@ -837,7 +836,7 @@ struct bg_ctx {
     const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
     int prep_warp = 0;              // BG_PREP=warp: draw + project the samples with the warp-per-sample k_prepare
-    int prep_ctas_per_sm[2][BG_MAX_T + 1] = {};   // k_prepare_tps: resident CTAs per SM by (word size, t), 0 = not asked yet
+    int prep_ctas_per_sm[2][2][BG_MAX_T + 1] = {};   // k_prepare_tps: resident CTAs per SM by (word size, CTA size, t), 0 = not asked yet
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
     bg_projector* d_P = nullptr;
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1] pair count
@@ -853,6 +852,25 @@ struct bg_ctx {
     // the next job can be staged while the previous job (and its upload) is still in flight
     bg_projector* h_stage = nullptr; cudaEvent_t ev_stage[2] = {nullptr, nullptr}; unsigned stage_seq = 0;
     bg_projector h_P[2];            // what d_P holds (a repeated prepare with the same content keeps the captured graph)
+    bool P_valid = false;
+    bg_projector cur_P[2];          // the prepared job's projectors (host copy)
+    // Overlap mode (few samples per GPU: the draw + projection kernel cannot fill the machine and is latency-bound): the
+    // jobs in the odd slot run on a stream and buffers of their own (`alt`, swapped in around their calls), so that
+    // k_prepare_tps of job i+1 runs beside the pair kernel of job i instead of behind it.
+    struct JobSet {
+        cudaStream_t stream = nullptr;
+        SampleRec* d_recs = nullptr; size_t recs_cap = 0;
+        long long* d_zw = nullptr; size_t zw_cap = 0;
+        long long* d_zw2 = nullptr; size_t zw2_cap = 0;
+        double* d_per = nullptr; size_t per_cap = 0;
+        double* d_per2 = nullptr; size_t per2_cap = 0;
+        bg_projector* d_P = nullptr; double* d_partials = nullptr; unsigned int* d_ticket = nullptr;
+        bg_projector h_P[2]; bool P_valid = false;
+    } alt;
+    bool alt_in = false;            // alt is swapped into the fields above
+    int overlap_mode = -1;          // BG_OVERLAP: 1 always, 0 never, -1 when a job has fewer than OVERLAP_WARPS_PER_SM warps of prepare work per SM
+    bool overlap = false;           // the prepared job runs in overlap mode
+    int per_set = 0;                // which set holds the per-sample values of the last finished job
     bool phase_events = false;
     int cur = 0;                    // projector being launched (selects counters / events / d_P slot)
     // the prepared job replayed as one CUDA graph (BG_GRAPH=0 disables)
@@ -894,6 +912,26 @@ static cudaError_t rec_event(bg_ctx* ctx, cudaEvent_t ev) {
 static void drop_graph(bg_ctx* ctx) {
     for (int sl = 0; sl < 2; sl++) if (ctx->gexecs[sl]) { cudaGraphExecDestroy(ctx->gexecs[sl]); ctx->gexecs[sl] = nullptr; }
 }
+
+// exchange the job-owned resources of ctx with the alternate set
+static void swap_set(bg_ctx* ctx) {
+    bg_ctx::JobSet& a = ctx->alt;
+    std::swap(ctx->stream, a.stream);
+    std::swap(ctx->d_recs, a.d_recs); std::swap(ctx->recs_cap, a.recs_cap);
+    std::swap(ctx->d_zw, a.d_zw); std::swap(ctx->zw_cap, a.zw_cap);
+    std::swap(ctx->d_zw2, a.d_zw2); std::swap(ctx->zw2_cap, a.zw2_cap);
+    std::swap(ctx->d_per, a.d_per); std::swap(ctx->per_cap, a.per_cap);
+    std::swap(ctx->d_per2, a.d_per2); std::swap(ctx->per2_cap, a.per2_cap);
+    std::swap(ctx->d_P, a.d_P); std::swap(ctx->d_partials, a.d_partials); std::swap(ctx->d_ticket, a.d_ticket);
+    std::swap(ctx->h_P[0], a.h_P[0]); std::swap(ctx->h_P[1], a.h_P[1]); std::swap(ctx->P_valid, a.P_valid);
+    ctx->alt_in = !ctx->alt_in;
+}
+struct SetGuard {               // the alternate set for the duration of a scope
+    bg_ctx* ctx; bool on;
+    SetGuard(bg_ctx* c, bool use_alt) : ctx(c), on(use_alt) { if (on) swap_set(ctx); }
+    ~SetGuard() { if (on) swap_set(ctx); }
+};
+static const int OVERLAP_WARPS_PER_SM = 8;
 
 template <typename T> static int ensure(bg_ctx* ctx, T** p, size_t* cap, size_t need) {
     if (!(*cap >= need && *p)) drop_graph(ctx);        // a captured graph holds the old pointers
@@ -953,6 +991,14 @@ extern "C" int bg_init(bg_ctx** out, int device) {
         for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) cudaEventCreate(&ctx->evps[sl][a][b]);
     }
     cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking);
+    if (cudaStreamCreateWithFlags(&ctx->alt.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->alt.d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->alt.d_partials, 64 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->alt.d_ticket, 2 * sizeof(unsigned int)) != cudaSuccess) {
+        int r = fail(nullptr, "bg_init: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx; return r;
+    }
+    cudaMemset(ctx->alt.d_ticket, 0, 2 * sizeof(unsigned int));
     if (cudaMalloc((void**)&ctx->d_P, 2 * sizeof(bg_projector)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void**)&ctx->h_out, 32 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
@@ -976,6 +1022,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e8 = getenv("BG_SHB")) ctx->use_shb = atoi(e8) != 0;
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e9 = getenv("BG_PREP")) ctx->prep_warp = strcmp(e9, "warp") == 0;
+    if (const char* e10 = getenv("BG_OVERLAP")) ctx->overlap_mode = atoi(e10) != 0;
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) { ctx->items_factor = v; ctx->items_factor_set = true; } }
     *out = ctx;
     return 0;
@@ -995,6 +1042,10 @@ extern "C" void bg_shutdown(bg_ctx* ctx) {
         for (int a = 0; a < 2; a++) for (int b = 0; b < 3; b++) if (ctx->evps[sl][a][b]) cudaEventDestroy(ctx->evps[sl][a][b]);
         if (ctx->gexecs[sl]) cudaGraphExecDestroy(ctx->gexecs[sl]);
     }
+    if (ctx->alt_in) swap_set(ctx);
+    cudaFree(ctx->alt.d_recs); cudaFree(ctx->alt.d_zw); cudaFree(ctx->alt.d_zw2); cudaFree(ctx->alt.d_per); cudaFree(ctx->alt.d_per2);
+    cudaFree(ctx->alt.d_P); cudaFree(ctx->alt.d_partials); cudaFree(ctx->alt.d_ticket);
+    if (ctx->alt.stream) cudaStreamDestroy(ctx->alt.stream);
     if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1109,6 +1160,7 @@ extern "C" int bg_set_decomposition(bg_ctx* ctx, int t, int exact, int k, const 
         for (int j = 0; same && !exact && j < k; j++) same = (L_rows[j] & maskt) == ctx->L[j];
         if (same) return 0;
     }
+    CK(cudaStreamSynchronize(ctx->alt.stream));     // a job on the alternate stream may still be reading the old tables
     size_t chi;
     if (exact) {
         const int size = (t + 1) / 2;
@@ -1227,17 +1279,17 @@ template <int NS> static int launch_prepare_ns(bg_ctx* ctx, int src, const PrepA
     return 0;
 }
 // k_prepare_tps: as many CTAs as are resident at once (occupancy x SMs), at most one warp per group of 32 samples
-template <typename W> static int launch_prepare_tps(bg_ctx* ctx, const PrepArgs& a) {
-    const size_t smem = prep_tps_smem<W>(a.t);
-    int& per_sm = ctx->prep_ctas_per_sm[sizeof(W) == 8][a.t];
+template <typename W, int THREADS> static int launch_prepare_tps(bg_ctx* ctx, const PrepArgs& a) {
+    const size_t smem = prep_tps_smem<W, THREADS>(a.t);
+    int& per_sm = ctx->prep_ctas_per_sm[sizeof(W) == 8][THREADS == 32][a.t];
     if (per_sm == 0) {
-        CK(cudaFuncSetAttribute(k_prepare_tps<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prepare_tps<W>, BG_PREP_THREADS, smem));
+        CK(cudaFuncSetAttribute(k_prepare_tps<W, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prepare_tps<W, THREADS>, THREADS, smem));
         if (per_sm < 1) return fail(ctx, "k_prepare_tps does not fit an SM at t = %d", a.t);
     }
-    const int groups = (a.n_samples + 31) / 32, wpb = BG_PREP_THREADS / 32;
+    const int groups = (a.n_samples + 31) / 32, wpb = THREADS / 32;
     const int blocks = std::max(1, std::min((groups + wpb - 1) / wpb, ctx->sm_count * per_sm));
-    k_prepare_tps<W><<<blocks, BG_PREP_THREADS, smem, ctx->stream>>>(a);
+    k_prepare_tps<W, THREADS><<<blocks, THREADS, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     return 0;
@@ -1249,8 +1301,10 @@ static int launch_prepare(bg_ctx* ctx, int src, PrepArgs a) {
     a.shb = (ctx->shb_plan.ok && src != SRC_TERMS) ? 1 : 0;     // SRC_TERMS = the exact-norm path (tri mode): generic kernels
     if (!a.P2) a.n_first = a.n_samples;
     a.n_warp_routed = CNT(ctx) + 4 * ctx->cur + 2;
-    if (src == SRC_RNG && a.project && !a.raw_out && !ctx->prep_warp)
-        return a.t <= 32 ? launch_prepare_tps<uint32_t>(ctx, a) : launch_prepare_tps<uint64_t>(ctx, a);
+    if (src == SRC_RNG && a.project && !a.raw_out && !ctx->prep_warp) {
+        if (ctx->overlap) return a.t <= 32 ? launch_prepare_tps<uint32_t, 32>(ctx, a) : launch_prepare_tps<uint64_t, 32>(ctx, a);
+        return a.t <= 32 ? launch_prepare_tps<uint32_t, 64>(ctx, a) : launch_prepare_tps<uint64_t, 64>(ctx, a);
+    }
     return a.t <= 32 ? launch_prepare_ns<1>(ctx, src, a) : launch_prepare_ns<2>(ctx, src, a);
 }
 
@@ -1408,6 +1462,26 @@ static double clifford_closed_form(const bg_projector* P) {
     return sum / (1 + (double)P->nstabs);
 }
 
+// d_P of the set that is swapped in := the prepared job's projectors, through a pinned staging copy, asynchronously on
+// that set's stream (ordered behind the job that may still be reading d_P there); the staging copies alternate, so the
+// projectors of the next job can be staged while the previous upload is still in flight.
+static int sync_projectors(bg_ctx* ctx) {
+    const int nproj = ctx->nproj;
+    bool same = ctx->P_valid;
+    for (int j = 0; same && j < nproj; j++) same = memcmp(&ctx->h_P[j], &ctx->cur_P[j], sizeof(bg_projector)) == 0;
+    if (same) return 0;
+    const unsigned ss = ctx->stage_seq++ & 1u;
+    CK(cudaEventSynchronize(ctx->ev_stage[ss]));     // the upload before last has left this staging set
+    bg_projector* hs = ctx->h_stage + 2 * ss;
+    for (int j = 0; j < nproj; j++) hs[j] = ctx->cur_P[j];
+    CK(cudaMemcpyAsync(ctx->d_P, hs, (size_t)nproj * sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_stage[ss], ctx->stream));
+    for (int j = 0; j < nproj; j++) ctx->h_P[j] = ctx->cur_P[j];
+    ctx->P_valid = true;
+    ctx->stats.h2d_bytes += (uint64_t)nproj * sizeof(bg_projector);
+    return 0;
+}
+
 static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* Ps, uint64_t samples, int bins,
                              const uint64_t* seeds) {
     if (!ctx) return fail(nullptr, "bg_sampled_prepare: null ctx");
@@ -1421,31 +1495,31 @@ static int sampled_prepare_n(bg_ctx* ctx, int nproj, const bg_projector* const* 
     CK(cudaSetDevice(ctx->device));
     const uint64_t mine = shard_count(samples, ctx->rank, ctx->world);
     if (mine > (1ull << 30)) return fail(ctx, "bg_sampled_prepare: %llu samples per rank is too many", (unsigned long long)mine);
-    // the projectors go through a pinned staging copy, asynchronously on the job's stream (the kernels read d_P when
-    // they run, so a captured graph stays valid); a job of the same shape and seeds keeps its graph
+    // a job of the same shape and seeds keeps its captured graph (the kernels read d_P when they run)
     bool same_shape = ctx->prepared && ctx->nproj == nproj && ctx->samples == samples && ctx->bins == bins;
     for (int j = 0; same_shape && j < nproj; j++) same_shape = ctx->seeds[j] == seeds[j];
-    if (!same_shape && ctx->run_seq != ctx->fin_seq) {   // an unfinished job of another shape: its buffers are about to change
-        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->cstream));
+    // overlap mode: a fused two-projector job whose draw + projection is less than OVERLAP_WARPS_PER_SM warps per SM
+    const bool fusable = ctx->fuse2 && nproj == 2 && bins == 1 && ctx->use_graph && !ctx->prep_warp && !ctx->force_warp;
+    const bool want_overlap = fusable && (ctx->overlap_mode == 1 ||
+        (ctx->overlap_mode < 0 && 2 * mine <= (uint64_t)32 * OVERLAP_WARPS_PER_SM * (uint64_t)ctx->sm_count));
+    if ((!same_shape || want_overlap != ctx->overlap) && ctx->run_seq != ctx->fin_seq) {
+        // an unfinished job of another shape: its buffers are about to change
+        CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->alt.stream)); CK(cudaStreamSynchronize(ctx->cstream));
         ctx->fin_seq = ctx->run_seq;
     }
-    if (!same_shape && ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj)) return 1;
-    bool same_P = same_shape;
-    for (int j = 0; same_P && j < nproj; j++) same_P = memcmp(&ctx->h_P[j], Ps[j], sizeof(bg_projector)) == 0;
-    ctx->stats.h2d_bytes = 0;
-    if (!same_P) {
-        // New projectors for a job of the same shape may be staged while the previous job is still in flight: the
-        // upload is ordered on the job's stream behind that job's kernels, and the staging sets alternate.
-        const unsigned ss = ctx->stage_seq++ & 1u;
-        CK(cudaEventSynchronize(ctx->ev_stage[ss]));     // the upload before last has left this staging set
-        bg_projector* hs = ctx->h_stage + 2 * ss;
-        for (int j = 0; j < nproj; j++) hs[j] = *Ps[j];
-        CK(cudaMemcpyAsync(ctx->d_P, hs, (size_t)nproj * sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_stage[ss], ctx->stream));
-        ctx->stats.h2d_bytes = (uint64_t)nproj * sizeof(bg_projector);
-    }
+    if (want_overlap != ctx->overlap) { drop_graph(ctx); ctx->overlap = want_overlap; }
+    const size_t nrec = (size_t)std::max<uint64_t>(mine, 1) * (size_t)nproj;
+    if (!same_shape && ensure_sample_buffers(ctx, nrec)) return 1;
+    if (ctx->overlap) { SetGuard g(ctx, true); if (ensure_sample_buffers(ctx, nrec)) return 1; }
     ctx->nproj = nproj; ctx->samples = samples; ctx->bins = bins;
-    for (int j = 0; j < nproj; j++) { ctx->seeds[j] = seeds[j]; ctx->h_P[j] = *Ps[j]; }
+    for (int j = 0; j < nproj; j++) { ctx->seeds[j] = seeds[j]; ctx->cur_P[j] = *Ps[j]; }
+    // the projectors go to the set the next bg_sampled_run uses (bg_sampled_run checks again: a job that is run many
+    // times alternates between the sets)
+    ctx->stats.h2d_bytes = 0;
+    {
+        SetGuard g(ctx, ctx->overlap && (ctx->run_seq & 1u));
+        if (sync_projectors(ctx)) return 1;
+    }
     ctx->prepared = true; ctx->per_valid = false;
     if (!same_shape) drop_graph(ctx);
     return 0;
@@ -1561,6 +1635,8 @@ extern "C" int bg_sampled_run(bg_ctx* ctx) {
     if (ctx->bins > 4) return fail(ctx, "bg_sampled_run: split-phase API supports at most 4 bins (use bg_sampled_norm)");
     if (ctx->run_seq - ctx->fin_seq >= 2) return fail(ctx, "bg_sampled_run: two jobs already in flight (call bg_sampled_finish)");
     ctx->slot = (int)(ctx->run_seq & 1u);
+    SetGuard set_guard(ctx, ctx->overlap && ctx->slot == 1);      // overlap mode: the odd slot's own stream and buffers
+    if (sync_projectors(ctx)) { ctx->slot = 0; return 1; }        // (no-op unless this set last held other projectors)
     int rc = 0;
     if (!ctx->use_graph) {
         ctx->stats.launches = 0;
@@ -1617,6 +1693,7 @@ static int collect_stats(bg_ctx* ctx, int nproj, bool counters_in_h_out) {
     CK(cudaEventElapsedTime(&ms, EV0(ctx), EV1(ctx)));
     ctx->stats.kernel_ms = ms;
     ctx->stats.prepare_ms = ctx->stats.pairs_ms = 0;
+    ctx->stats.overlapped = 0;
     if (ctx->phase_events) {
         for (int pj = 0; pj < nproj; pj++) {
             float a = 0, b = 0;
@@ -1648,7 +1725,9 @@ static int sampled_finish_n(bg_ctx* ctx, double* out) {
     ctx->stats.pair_launches = fused2(ctx) ? 1 : (uint64_t)ctx->nproj * ctx->bins;
     ctx->phase_events = true;
     ctx->per_valid = true;
+    ctx->per_set = (ctx->overlap && ctx->slot == 1) ? 1 : 0;
     const int rc = collect_stats(ctx, ctx->nproj, true);
+    ctx->stats.overlapped = ctx->overlap ? 1 : 0;
     for (int pj = 0; pj < ctx->nproj && !rc; pj++) {
         std::vector<double> v(ctx->bins);
         for (int b = 0; b < ctx->bins; b++) v[b] = HOUT(ctx)[4 * pj + b] / (double)ctx->samples;   // total/samples (innerprod.c:83)
@@ -1699,7 +1778,7 @@ extern "C" int bg_sampled_norm(bg_ctx* ctx, const bg_projector* P, uint64_t samp
     ctx->stats.kernel_ms = total_ms; ctx->stats.pairs = total_pairs; ctx->stats.launches = launches;
     ctx->stats.prepare_ms = prep_ms; ctx->stats.pairs_ms = pair_ms;
     ctx->stats.d2h_bytes = bins * sizeof(double);
-    ctx->per_valid = true;
+    ctx->per_valid = true; ctx->per_set = 0;
     *out = median_of_bins(v);
     return 0;
 }
@@ -1735,6 +1814,7 @@ extern "C" int bg_sampled_per_sample(bg_ctx* ctx, int projector, uint64_t first,
     if (!fused2(ctx) && projector != ctx->nproj - 1)
         return fail(ctx, "bg_sampled_per_sample: only the last projector's values are kept for this job (bins > 1 or BG_FUSE2=0)");
     const size_t off = fused2(ctx) ? (size_t)projector * (size_t)mine : 0;
+    SetGuard set_guard(ctx, ctx->per_set == 1);
     CK(cudaMemcpy(out, ctx->d_per + off + first, count * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -1772,7 +1852,7 @@ static int exact_norm_parts(bg_ctx* ctx, const bg_projector* P, double s[2]) {
     const uint64_t mine = shard_count(chi, ctx->rank, ctx->world);
     const int n = (int)mine;
     if (ensure_sample_buffers(ctx, (size_t)std::max<uint64_t>(mine, 1))) return 1;
-    ctx->prepared = false;                       // d_P no longer holds the prepared job's projectors
+    ctx->prepared = false; ctx->P_valid = false; // d_P no longer holds the prepared job's projectors
     CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes = sizeof(bg_projector);
     ctx->stats.launches = 0;
@@ -1864,7 +1944,7 @@ extern "C" int bg_sampled_norm_from_states(bg_ctx* ctx, const bg_projector* P, i
     DevBuf<bg_state> dth; DevBuf<int32_t> depm;
     CK(dth.alloc(n_states));
     CK(cudaMemcpyAsync(dth, thetas, n_states * sizeof(bg_state), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prepared = false;                       // d_P / the sample buffers no longer belong to the prepared job
+    ctx->prepared = false; ctx->P_valid = false; // d_P / the sample buffers no longer belong to the prepared job
     if (project) CK(cudaMemcpyAsync(ctx->d_P, P, sizeof(bg_projector), cudaMemcpyHostToDevice, ctx->stream));
     if (epm) {
         CK(depm.alloc(n_states * chi * 3));

@@ -178,6 +178,9 @@ typedef struct bg_stats {
     uint64_t d2h_bytes;        /* device->host bytes moved by the last call                       */
     double   prepare_ms;       /* ... of which k_prepare (theta draw + projection + ambient form)  */
     double   pairs_ms;         /* ... of which the pair kernels (the L x chi loop proper)          */
+    uint64_t overlapped;       /* 1: the job ran in overlap mode (few samples per GPU, see bg_sampled_run):
+                                  consecutive jobs run on two streams, so prepare_ms / pairs_ms of one job
+                                  include the time its kernels shared the GPU with the other job's      */
 } bg_stats;
 int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
 
@@ -187,7 +190,13 @@ int  bg_get_stats(const bg_ctx* ctx, bg_stats* out);
 int  bg_sampled_prepare(bg_ctx* ctx, const bg_projector* P, uint64_t samples, int bins, uint64_t seed);
 int  bg_sampled_run(bg_ctx* ctx);                       /* async: kernels on ctx's stream (captured once into a CUDA
                                                            graph, then replayed), all-reduce + read-back on a side
-                                                           stream.  Up to TWO runs may be in flight.             */
+                                                           stream.  Up to TWO runs may be in flight.  A fused
+                                                           two-projector job with few samples per GPU (its draw +
+                                                           projection kernel cannot fill the machine) runs in OVERLAP
+                                                           mode: every second run goes to an internal stream with
+                                                           buffers of its own, so that the draw + projection of run
+                                                           i+1 shares the GPU with the pair kernel of run i
+                                                           (BG_OVERLAP=0 / 1 forces it off / on).                 */
 int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* wait for the OLDEST run in flight     */
 
 /* Numerator and denominator of one probability() evaluation together — both projectors against the

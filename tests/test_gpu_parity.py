@@ -417,10 +417,26 @@ def test_pipelined_runs_two_in_flight(be):
         be.sampled_finish2(1.0)               # nothing in flight
 
 
-def test_new_projectors_staged_while_a_job_is_in_flight(be):
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_new_projectors_staged_while_a_job_is_in_flight(overlap):
     """The end-to-end pipeline bench.py times: bg_sampled_prepare2 with NEW projector bytes while the previous job of
     the same shape has not been collected (staging sets alternate, the upload is ordered behind the running job on
-    its stream).  Each job must return what the same projectors give one call at a time."""
+    its stream).  Each job must return what the same projectors give one call at a time — with consecutive jobs on
+    one stream (BG_OVERLAP=0) and in overlap mode (every second job on a stream and buffers of its own, which is what
+    a job with few samples per GPU gets by default)."""
+    import circuitsimulator_b200 as bg
+    os.environ["BG_OVERLAP"] = overlap
+    try:
+        be = bg.Backend(0)
+    finally:
+        del os.environ["BG_OVERLAP"]
+    try:
+        _staged_in_flight(be, overlap == "1")
+    finally:
+        be.close()
+
+
+def _staged_in_flight(be, overlapped):
     import circuitsimulator_b200 as bg
     cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t16_bit6.txt"))
     be.set_decomposition(cfg["t"], True)
@@ -438,6 +454,14 @@ def test_new_projectors_staged_while_a_job_is_in_flight(be):
         got.append(be.sampled_finish2(1.0))
     got.append(be.sampled_finish2(1.0))
     assert got == want
+    assert be.stats()["overlapped"] == (1 if overlapped else 0)
+    # the per-sample values of the last finished job come from the set it ran in
+    per = be.sampled_per_sample(0, 0, 5000)
+    assert abs(per.sum() / 5000 - want[-1][0]) <= 1e-12 * abs(want[-1][0])
+    # a prepared job replayed many times alternates between the sets
+    be.sampled_run()
+    be.sampled_run()
+    assert be.sampled_finish2(1.0) == want[-1] and be.sampled_finish2(1.0) == want[-1]
     # a job of another shape drops what is in flight (its buffers change) instead of returning stale numbers
     be.sampled_run()
     be.sampled_prepare2(g, h, 1234, 1, 7, 8)
