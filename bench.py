@@ -644,6 +644,8 @@ def main():
         barrier()
         return allmax(e0.elapsed_time(e1))
 
+    timed_block(max(3, args.warmup), False)                # warm-up in the timed pattern too (two jobs in flight; in overlap
+                                                           # mode the second slot's stream, buffers and graph see their first use)
     ms = timed_block(args.steps, True)                     # THE timed region: exactly K steps
     # the pairs the device actually evaluated (annihilated samples evaluate none), all ranks
     pairs_total = allsum(acc["pairs"])
