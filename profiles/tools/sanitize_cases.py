@@ -3,7 +3,10 @@
     compute-sanitizer --tool racecheck python profiles/tools/sanitize_cases.py
 Cases: smoke() (t=16 exact decomposition, k_prepare + k_pairs_tpp<u32>), config 4 at 192 samples (k_pairs_shb, TMA
 staging, warp-shared reduced forms), the same with BG_SHB=0 (k_pairs_tpp<u64>), low-dimensional thetas (MANYC
-instantiation: pivot history in shared memory), the exact-norm path (tri mode), the warp-per-pair kernel."""
+instantiation: pivot history in shared memory), the exact-norm path (tri mode), the warp-per-pair kernel; the draw +
+projection one thread per sample (k_prepare_tps: 64-thread CTAs, 32- and 64-bit words; the default of every sampled job
+above), one warp per sample (BG_PREP=warp), and overlap mode (BG_OVERLAP=1: 32-thread CTAs, two jobs in flight on two
+streams with new projectors staged while a job runs)."""
 import os
 import sys
 
@@ -22,7 +25,7 @@ cfg, Gd, Hd, samples, k, desc = bench.load_config(bench.DEFAULT_CONFIG)
 t = cfg["t"]
 L = bench.fixed_L(k, t)
 G, H = bg.Projector.make(*Gd), bg.Projector.make(*Hd)
-for env in ({}, {"BG_SHB": "0"}, {"BG_KERNEL": "warp"}):
+for env in ({}, {"BG_SHB": "0"}, {"BG_KERNEL": "warp"}, {"BG_PREP": "warp"}):
     os.environ.update(env)
     be = bg.Backend(0)
     for key in env:
@@ -31,6 +34,20 @@ for env in ({}, {"BG_SHB": "0"}, {"BG_KERNEL": "warp"}):
     n = 32 if env.get("BG_KERNEL") else 192
     print(env, "sampled_norm2:", be.sampled_norm2(G, H, n, 1, 3, 4, 1.0), be.stats()["pairs"], "pairs", flush=True)
     be.close()
+os.environ["BG_OVERLAP"] = "1"
+be = bg.Backend(0)
+del os.environ["BG_OVERLAP"]
+be.set_decomposition(t, False, L)
+got = []
+be.sampled_prepare2(G, H, 100, 1, 3, 4)
+be.sampled_run()
+for a, b in ((H, G), (G, G), (G, H)):
+    be.sampled_prepare2(a, b, 100, 1, 3, 4)
+    be.sampled_run()
+    got.append(be.sampled_finish2(1.0))
+got.append(be.sampled_finish2(1.0))
+print("overlap mode, two jobs in flight:", got, be.stats()["overlapped"], flush=True)
+be.close()
 be = bg.Backend(0)
 o = Oracle()
 tt = 12
