@@ -835,6 +835,7 @@ struct bg_ctx {
 #endif                          // BG_LAM_MAX: parity checks carried as Lagrange variables (0: pivot every check per term)
     const int tpp_warps = BG_TPP_WARPS;   // warps per CTA of k_pairs_tpp
     int force_warp = 0;             // BG_KERNEL=warp: evaluate everything with the warp-per-pair kernel
+    int pieces_override = 0;        // BG_PIECES: pieces of the last wave's samples in k_pairs_shb (0: chosen by launch_pairs)
     int prep_warp = 0;              // BG_PREP=warp: draw + project the samples with the warp-per-sample k_prepare
     int prep_ctas_per_sm[2][2][BG_MAX_T + 1] = {};   // k_prepare_tps: resident CTAs per SM by (word size, CTA size, t), 0 = not asked yet
     int fuse2 = 1;                  // BG_FUSE2=0: one launch sequence per projector instead of one for both
@@ -1023,6 +1024,7 @@ extern "C" int bg_init(bg_ctx** out, int device) {
     if (const char* e3 = getenv("BG_KERNEL")) ctx->force_warp = strcmp(e3, "warp") == 0;
     if (const char* e9 = getenv("BG_PREP")) ctx->prep_warp = strcmp(e9, "warp") == 0;
     if (const char* e10 = getenv("BG_OVERLAP")) ctx->overlap_mode = atoi(e10) != 0;
+    if (const char* e11 = getenv("BG_PIECES")) ctx->pieces_override = std::max(0, atoi(e11));
     if (const char* e2 = getenv("BG_ITEMS_FACTOR")) { int v = atoi(e2); if (v >= 1 && v <= 1024) { ctx->items_factor = v; ctx->items_factor_set = true; } }
     *out = ctx;
     return 0;
@@ -1394,6 +1396,7 @@ static int launch_pairs(bg_ctx* ctx, PairArgs a) {
                 const int rw = ctx->sm_count * 30;                               // resident warps of k_pairs_shb (10 CTAs x 3 warps)
                 int pieces = 4;
                 while ((long long)std::min(b.n_samples, rw) * pieces < 2LL * rw && pieces < groups) pieces *= 2;
+                if (ctx->pieces_override > 0) pieces = ctx->pieces_override;
                 pieces = std::max(1, std::min(pieces, groups));
                 b.piece = (groups + pieces - 1) / pieces * gran;
                 b.pieces = (b.nterms + b.piece - 1) / b.piece;
