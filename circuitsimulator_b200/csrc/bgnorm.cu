@@ -932,7 +932,7 @@ struct SetGuard {               // the alternate set for the duration of a scope
     SetGuard(bg_ctx* c, bool use_alt) : ctx(c), on(use_alt) { if (on) swap_set(ctx); }
     ~SetGuard() { if (on) swap_set(ctx); }
 };
-static const int OVERLAP_WARPS_PER_SM = 8;
+static const int OVERLAP_WARPS_PER_SM = 16;
 
 template <typename T> static int ensure(bg_ctx* ctx, T** p, size_t* cap, size_t need) {
     if (!(*cap >= need && *p)) drop_graph(ctx);        // a captured graph holds the old pointers
