@@ -49,6 +49,11 @@ struct ShbBasis {
         return 0;
     }
     bool add(uint32_t v) { v = reduce(v); if (!v) return false; b[31 - __builtin_clz(v)] = v; return true; }
+    // the representative of v + span with a zero at every pivot position (the same for all members of a coset)
+    uint32_t residue(uint32_t v) const {
+        for (int h = 31; h >= 0; h--) if (b[h] && ((v >> h) & 1u)) v ^= b[h];
+        return v;
+    }
 };
 
 // terms_nat[i] = x~_i in natural order (bit q = variable q), L = the k rows.  Returns plan.ok = 1 on success.
@@ -65,7 +70,7 @@ static inline ShbPlan shb_make_plan(int t, int k, const std::vector<uint64_t>& L
     std::vector<int> best;
     {
         std::vector<int> idx(std::max(r, 1));
-        long long budget = 400000;                       // ~0.1 s at worst; a random L is found within a few hundred tries
+        long long budget = 1000;                         // lexicographic fallback after the randomised search (~2 ms in all when no plan exists)
         auto count_inside = [&](const ShbBasis& B, std::vector<int>& inside) {
             inside.clear();
             for (int c = 0; c < t; c++) if (B.reduce(col[c]) == 0) inside.push_back(c);
@@ -76,9 +81,34 @@ static inline ShbPlan shb_make_plan(int t, int k, const std::vector<uint64_t>& L
         } else if (r >= nh) {
             for (int c = t - nh; c < t; c++) best.push_back(c);       // any nh columns span at most nh <= r dimensions
         } else {
+            // First a randomised search (deterministic: seeded by L).  r - 1 random columns span U; every other column
+            // lies in U or in one of the cosets U + c, and a coset that holds m columns gives the subspace U + <c> with
+            // |inside U| + m columns — all choices of the r-th generator are judged at once.  For a random 9 x 40 L a
+            // hit takes ~40 tries of ~1 us where the lexicographic enumeration below needs thousands of dependent ones.
+            uint64_t seed = 0x9E3779B97F4A7C15ull;
+            for (int j = 0; j < k; j++) seed = (seed ^ L[j]) * 0xD1342543DE82EF95ull + 1ull;
+            auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return seed; };
+            std::vector<uint32_t> res(t);
+            for (int tries = 0; tries < 1500 && best.empty(); tries++) {
+                ShbBasis B;
+                for (int i = 0; i < r - 1; i++) B.add(col[(int)(rnd() % (uint64_t)t)]);
+                int inside_u = 0, nres = 0;
+                for (int c = 0; c < t; c++) { const uint32_t v = B.residue(col[c]); if (v) res[nres++] = v; else inside_u++; }
+                std::sort(res.begin(), res.begin() + nres);
+                int run = 0, best_run = 0; uint32_t best_v = 0;
+                for (int i = 0; i < nres; i++) {
+                    run = (i > 0 && res[i] == res[i - 1]) ? run + 1 : 1;
+                    if (run > best_run) { best_run = run; best_v = res[i]; }
+                }
+                if (inside_u + best_run < nh) continue;
+                if (best_v) B.add(best_v);
+                std::vector<int> in;
+                count_inside(B, in);
+                if ((int)in.size() >= nh) best = in;
+            }
             for (int i = 0; i < r; i++) idx[i] = i;
             std::vector<int> inside;
-            while (budget-- > 0) {
+            while ((int)best.size() < nh && budget-- > 0) {
                 ShbBasis B;
                 for (int i = 0; i < r; i++) B.add(col[idx[i]]);
                 count_inside(B, inside);
@@ -119,13 +149,15 @@ static inline ShbPlan shb_make_plan(int t, int k, const std::vector<uint64_t>& L
         if (32 - __builtin_popcount((uint32_t)tp[i]) < SHB_RELOC) return pl;       // every thread needs SHB_RELOC free low slots
     }
     pl.nat.resize(chi);
-    for (size_t i = 0; i < chi; i++) pl.nat[i] = (int32_t)i;
-    // by pattern; inside a class by popcount of the low word (equal work for neighbouring lanes)
-    std::stable_sort(pl.nat.begin(), pl.nat.end(), [&](int32_t x, int32_t y) {
-        const uint32_t px = (uint32_t)(tp[x] >> 32), py = (uint32_t)(tp[y] >> 32);
-        if (px != py) return px < py;
-        return __builtin_popcount((uint32_t)tp[x]) > __builtin_popcount((uint32_t)tp[y]);
-    });
+    // by pattern; inside a class by popcount of the low word, largest first (equal work for neighbouring lanes); ties
+    // keep the natural order.  One sort of composite keys (pattern | 32 - popcount | index; chi <= 2^26).
+    {
+        std::vector<uint64_t> keys(chi);
+        for (size_t i = 0; i < chi; i++)
+            keys[i] = ((uint64_t)(uint32_t)(tp[i] >> 32) << 32) | ((uint64_t)(32 - __builtin_popcount((uint32_t)tp[i])) << 26) | (uint64_t)i;
+        std::sort(keys.begin(), keys.end());
+        for (size_t i = 0; i < chi; i++) pl.nat[i] = (int32_t)(keys[i] & 0x3ffffffull);
+    }
     pl.terms.resize(chi);
     for (size_t i = 0; i < chi; i++) pl.terms[i] = tp[pl.nat[i]];
     for (size_t i = 0; i + 31 < chi; i += 32)

@@ -471,6 +471,48 @@ def _staged_in_flight(be, overlapped):
     assert be.sampled_finish2(1.0) == be.sampled_norm2(g, h, 1234, 1, 7, 8, 1.0)
 
 
+def test_new_decomposition_of_the_same_shape_keeps_the_prepared_job(be):
+    """sampleQubits draws a new L for every probability() call.  bg_set_decomposition with another L of the same
+    (t, k) keeps the prepared job and its captured CUDA graphs (the tables change, no kernel argument does — the
+    relabelling of the shared high-block plan sits in device memory); the results must be those of a context that
+    has seen only that L.  Changing k or t in between must not leave anything stale either."""
+    import circuitsimulator_b200 as bg
+    cfg, G, H = parse_stream(os.path.join(GOLDEN, "streams", "hs_t40_k9_bit0.txt"))
+    t = cfg["t"]
+    g, h = to_bg(G), to_bg(H)
+    rs = np.random.RandomState(11)
+    Ls = [_bench_L(9, t)] + [[int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(9)] for _ in range(5)]
+    fresh = []
+    for L in Ls:
+        other = bg.Backend(0)
+        try:
+            other.set_decomposition(t, False, L)
+            fresh.append(other.sampled_norm2(g, h, 600, 1, 21, 22, 1.0))
+        finally:
+            other.close()
+    assert len(set(fresh)) == len(fresh)
+    for rounds in range(2):
+        for L, want in zip(Ls, fresh):
+            be.set_decomposition(t, False, L)
+            assert be.sampled_norm2(g, h, 600, 1, 21, 22, 1.0) == want
+    # split-phase, two in flight, L changing between the submissions
+    be.set_decomposition(t, False, Ls[0])
+    be.sampled_prepare2(g, h, 600, 1, 21, 22)
+    be.sampled_run()
+    be.set_decomposition(t, False, Ls[1])
+    be.sampled_prepare2(g, h, 600, 1, 21, 22)
+    be.sampled_run()
+    assert be.sampled_finish2(1.0) == fresh[0]
+    assert be.sampled_finish2(1.0) == fresh[1]
+    # another shape in between
+    be.set_decomposition(t, False, Ls[2][:8])
+    a = be.sampled_norm2(g, h, 600, 1, 21, 22, 1.0)
+    be.set_decomposition(t, False, Ls[2])
+    assert be.sampled_norm2(g, h, 600, 1, 21, 22, 1.0) == fresh[2]
+    be.set_decomposition(t, False, Ls[2][:8])
+    assert be.sampled_norm2(g, h, 600, 1, 21, 22, 1.0) == a
+
+
 def test_persistent_server_mode(tmp_path):
     """`bgbackend --serve <socket>` keeps the CUDA contexts alive across probability() calls; a client
     started with BG_SERVER=<socket> relays the same protocol."""
