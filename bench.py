@@ -559,8 +559,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU path")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")          # host-side waits (see the probability() leg)
 
     cfg, Gd, Hd, samples, k, desc = load_config(cfgname)
     t = cfg["t"]
@@ -740,6 +742,10 @@ def main():
         prob_s = probability_seconds(t, samples, k, exact, Gd, Hd, world)
         if prob_s is not None:
             prob_s["sample_qubits_phase_estimation"] = sample_qubits_seconds(world)
+    if cpu_group is not None:
+        # the other ranks wait on the HOST: an NCCL barrier would keep a spinning kernel on their GPUs, which are the
+        # GPUs the back end under test is running on (measured: 7.9 instead of 5.0 ms per served call at N = 2)
+        dist.barrier(group=cpu_group)
     barrier()
 
     if rank == 0:

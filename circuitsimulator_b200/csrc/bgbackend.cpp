@@ -477,7 +477,8 @@ static bool write_all(int fd, const char* p, size_t n) {
 // <socket>` keeps the contexts alive; a `bgbackend` started with BG_SERVER=<socket> only forwards its
 // instruction stream and relays the answer, so the drop-in protocol is unchanged.
 static int serve(const char* path, int gpus, int device0, bool chatter) {
-    Engine engine(gpus, device0, true);
+    const char* red = getenv("BG_REDUCE");          // the server keeps an NCCL communicator unless BG_REDUCE=host
+    Engine engine(gpus, device0, !(red && strcmp(red, "host") == 0));
     std::string err = engine.start();
     if (!err.empty()) { fprintf(stderr, "bgbackend --serve: %s\n", err.c_str()); return 1; }
     signal(SIGPIPE, SIG_IGN);                      // a client that goes away before reading its answer must not kill the server
