@@ -545,6 +545,17 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_tpp(PairArgs a) {
 #endif
 #define SHB_CLASS_WORDS ((32 + SHB_MAXHT + 3) & ~3)          // 16-byte aligned: the reduced rows are read with LDS.128
 #define SHB_WARP_WORDS (SHB_G * SHB_CLASS_WORDS)
+// the warp's 32-bit partial sums -> the sample's 64-bit accumulators (warp-uniform call)
+__device__ __forceinline__ void shb_flush(Zw32& zs, long long* zw, int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        long long v = (long long)zs.a[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += shfl_down_ll(v, d);
+        if (lane == 0 && v) atomicAdd((unsigned long long*)&zw[j], (unsigned long long)v);
+        zs.a[j] = 0;
+    }
+}
 __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -590,8 +601,10 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
         const int nlam = shb_load(r->J, r->Cw, r->Cpend, r->Cbeta, r->D1, r->D2, (uint32_t)r->Q, t, s_pm, f);
         const int k1 = r->k1;
         const uint32_t lam_bits = ((1u << nlam) - 1u) << s_pm.nh;
-        Zw z;
-        z.a[0] = z.a[1] = z.a[2] = z.a[3] = 0;
+        Zw32 zs;                                                // this thread's terms since the last flush (t <= 44: 32 bits do)
+        zs.a[0] = zs.a[1] = zs.a[2] = zs.a[3] = 0;
+        int nacc = 0;
+        static_assert(32 + SHB_MAXH <= ZW32_MAX_T, "Zw32 holds 2^(t/2+1) x ZW32_MAX_TERMS");
         for (int g = i0; g < i1; g += 32 * SHB_G) {             // SHB_G classes of 32 terms; every class has one high pattern
             ShbBatch sb;
             sb.red = my_red; sb.left = my_left; sb.k1 = k1; sb.nlam = nlam;
@@ -625,24 +638,20 @@ __global__ void __launch_bounds__(BG_TPP_THREADS) k_pairs_shb(PairArgs a) {
                 int e, p, m;
                 t_term_shb(rows, sb, term, nlmax, e, p, m);
                 __syncwarp();                                   // the lanes leave the elimination at different times
-                zw_add(z, e, p, m, sh_);
+                zw32_add(zs, e, p, m, sh_);
                 if (a.epm) {
                     int32_t* o3 = a.epm + ((size_t)idx * a.nterms + a.term_nat[ti]) * 3;
                     o3[0] = e; o3[1] = p; o3[2] = m & 7;
                 }
                 my_pairs++;
             }
+            nacc += SHB_G;
+            if (nacc > ZW32_MAX_TERMS - SHB_G && g + 32 * SHB_G < i1) {      // (an item of more than 128 terms per thread: k >= 13)
+                shb_flush(zs, a.zw + (size_t)idx * 4, lane);
+                nacc = 0;
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) z.a[j] += shfl_down_ll(z.a[j], d);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (z.a[j]) atomicAdd((unsigned long long*)&a.zw[(size_t)idx * 4 + j], (unsigned long long)z.a[j]);
-        }
+        shb_flush(zs, a.zw + (size_t)idx * 4, lane);
     }
     for (int d = 16; d > 0; d >>= 1) my_pairs += __shfl_down_sync(BG_FULL, my_pairs, d);
     if (lane == 0 && my_pairs) atomicAdd(a.pair_count, my_pairs);
