@@ -648,13 +648,16 @@ def main():
 
     timed_block(max(3, args.warmup), False)                # warm-up in the timed pattern too (two jobs in flight; in overlap
                                                            # mode the second slot's stream, buffers and graph see their first use)
-    ms = timed_block(args.steps, True)                     # THE timed region: exactly K steps
+    # THE timed region — exactly K steps between barrier + synchronize, max over ranks — five times; `value` is the
+    # median block (one block of K steps at N = 8 is 40 ms: a single stall of one rank moves it by several per cent).  The
+    # first block also reads the library's per-kernel CUDA-event times after every step (the roofline's kernel_ms).
+    first_ms = timed_block(args.steps, True)
     # the pairs the device actually evaluated (annihilated samples evaluate none), all ranks
     pairs_total = allsum(acc["pairs"])
     pairs_per_step = pairs_total / args.steps
+    block_ms = [first_ms] + [timed_block(args.steps, False) for _ in range(4)]
+    ms = sorted(block_ms)[len(block_ms) // 2]
     value = pairs_total / (ms * 1e-3)
-    # the same K-step region four more times: the spread of the measurement (median reported beside `value`)
-    block_ms = [ms] + [timed_block(args.steps, False) for _ in range(4)]
     # a timed region of a few ms is shorter than one nvidia-smi poll: keep the same load running
     # (untimed; the same number of steps on every rank) so that the sampler sees clocks under load
     if sum(block_ms) < 1500.0:
@@ -795,6 +798,8 @@ def main():
                 "pairs_per_step": pairs_per_step,
                 "blocks": {"n": len(block_ms), "steps_each": args.steps,
                            "ms_per_step": [b / args.steps for b in block_ms],
+                           "value_is": "the median block (every block is exactly K timed steps)",
+                           "first_block_ms_per_step": first_ms / args.steps,
                            "median_value": pairs_per_step * args.steps / (block_ms[len(block_ms) // 2] * 1e-3)},
                 "e2e": {"value": e2e_value, "unit": "inner products/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h,
