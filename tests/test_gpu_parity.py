@@ -763,13 +763,15 @@ def _backend_stream(name, samples=None, k=None):
 
 @pytest.mark.parametrize("env", [{"BG_KERNEL": "warp"}, {"BG_FUSE2": "0"}, {"BG_SHB": "0"}, {"BG_GRAPH": "0"},
                                  {"BG_ITEMS_FACTOR": "1"}, {"BG_CTAS_PER_SM": "2"}, {"BG_SHB": "0", "BG_LAM_MAX": "4"},
-                                 {"BG_SHB": "0", "BG_LAM_MAX": "0"}],
+                                 {"BG_SHB": "0", "BG_LAM_MAX": "0"}, {"BG_PREP": "warp"}, {"BG_OVERLAP": "1"},
+                                 {"BG_OVERLAP": "0"}, {"BG_PIECES": "2"}],
                          ids=lambda e: "_".join("%s=%s" % kv for kv in e.items()))
 def test_launch_variants_give_identical_sums(env):
     """Every default-off variant on the hardware: the warp-per-pair kernel (the north-star mapping, BG_KERNEL=warp),
     one launch sequence per projector (BG_FUSE2=0), the generic 64-bit kernel instead of the shared high-block one
     (BG_SHB=0) with theta's parity checks carried as Lagrange variables (BG_LAM_MAX=4) or pivoted per term (0), no CUDA
-    graph, other work partitions.  Per-sample sums are exact integers, so numerator and
+    graph, other work partitions, the warp-per-sample draw + projection kernel (BG_PREP=warp), overlap mode forced on
+    and off, another split of the last wave (BG_PIECES).  Per-sample sums are exact integers, so numerator and
     denominator must agree to the last bits (only the final fp64 sum over samples depends on the order)."""
     import circuitsimulator_b200 as bg
     text = _backend_stream("hs_t40_k9_bit0.txt", samples=2048)
