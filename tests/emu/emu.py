@@ -59,7 +59,15 @@ class Emu:
         lib.emu_work_counters.argtypes = [_P(C.c_ulonglong), C.c_int]
         lib.emu_prepare_both.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, _P(C.c_double), _P(Projector),
                                          _P(C.c_uint64), _P(C.c_uint64)]
+        lib.emu_shb_plan_check.argtypes = [C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_ulonglong)]
+        lib.emu_shb_plan_check.restype = C.c_int
         self.lib = lib
+
+    def shb_plan_check(self, t, L):
+        """(code, digest): 0 no plan, 1 a plan whose invariants hold, < 0 the invariant that fails (emu_lib.cpp)"""
+        rows = (C.c_uint64 * max(1, len(L)))(*[int(x) for x in L])
+        dg = C.c_ulonglong()
+        return self.lib.emu_shb_plan_check(t, len(L), rows, C.byref(dg)), dg.value
 
     def prepare_both(self, n, seed, bin_, sample, cdf, P):
         """One device-RNG sample projected by P: the SampleRec fields (136 uint64) as the warp-per-sample code and

@@ -348,6 +348,55 @@ int emu_terms_shb(const bg_state* theta, const bg_projector* P, int project, int
     return alive;
 }
 
+// The shared high-block plan of bg_shb_plan.h for one L: returns 0 (no plan), 1 (plan, every invariant holds) or a
+// negative code naming the invariant that fails.  digest receives a hash of the plan (the search is deterministic).
+int emu_shb_plan_check(int t, int k, const uint64_t* Lrows, unsigned long long* digest) {
+    std::vector<uint64_t> L(Lrows, Lrows + k), terms((size_t)1 << k);
+    const uint64_t maskt = t >= 64 ? ~0ull : ((1ull << t) - 1);
+    for (size_t i = 0; i < terms.size(); i++) {
+        uint64_t x = 0;
+        for (int j = 0; j < k; j++) if ((i >> (k - 1 - j)) & 1) x ^= L[j];
+        terms[i] = x & maskt;
+    }
+    ShbPlan pl = shb_make_plan(t, k, L, terms);
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    mix((unsigned long long)pl.ok);
+    if (!pl.ok) { if (digest) *digest = h; return 0; }
+    const size_t chi = terms.size();
+    if (pl.nh != t - 32 || pl.terms.size() != chi || pl.nat.size() != chi) return -1;
+    std::vector<char> seen(chi, 0);
+    for (size_t i = 0; i < chi; i++) {
+        const int32_t n = pl.nat[i];
+        if (n < 0 || (size_t)n >= chi || seen[n]) return -2;                      // nat is a permutation
+        seen[n] = 1;
+        if (pl.terms[i] != shb_permute_bits(terms[n], pl)) return -3;              // terms are the relabelled natural terms
+        if (pl.terms[i] >> t) return -4;
+        if (32 - __builtin_popcount((uint32_t)pl.terms[i]) < SHB_RELOC) return -5; // free low slots for the leftovers
+        mix(pl.terms[i]); mix((unsigned long long)n);
+    }
+    for (size_t i = 0; i < chi; i += 32) {
+        for (size_t j = 1; j < 32; j++)
+            if ((pl.terms[i + j] >> 32) != (pl.terms[i] >> 32)) return -6;          // one high pattern per class of 32
+    }
+    for (int i = 0; i < pl.nsw; i++) {
+        if (!(pl.swp[i] < 32 && pl.swq[i] >= 32 && pl.swq[i] < t)) return -8;       // every swap crosses the word boundary
+        for (int j = 0; j < i; j++) if (pl.swp[i] == pl.swp[j] || pl.swq[i] == pl.swq[j]) return -9;
+    }
+    // the high columns of L (after relabelling) span at most k - 5 dimensions: classes of at least 32 terms
+    {
+        ShbBasis B; int rk = 0;
+        for (int c = 32; c < t; c++) {
+            uint32_t col = 0;
+            for (int j = 0; j < k; j++) col |= (uint32_t)((shb_permute_bits(L[j] & maskt, pl) >> c) & 1ull) << j;
+            rk += B.add(col) ? 1 : 0;
+        }
+        if (rk > k - 5) return -10;
+    }
+    if (digest) *digest = h;
+    return 1;
+}
+
 int emu_expsum_selftest(int wordbits, unsigned long long seed, int trials) {
     return wordbits == 32 ? expsum_selftest<uint32_t>(seed, trials) : expsum_selftest<uint64_t>(seed, trials);
 }

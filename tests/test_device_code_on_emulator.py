@@ -289,3 +289,25 @@ def test_thread_per_sample_prepare_random_projectors(emu, oracle, t):
             seen_checks += bin(a[6]).count("1") > 3
     if t >= 8:
         assert seen_checks > 0 and seen_dead > 0
+
+
+@pytest.mark.parametrize("t,k,min_rate", [(33, 6, 0.99), (36, 8, 0.95), (40, 9, 0.95), (40, 12, 0.99), (44, 9, 0.0), (44, 13, 0.9)])
+def test_shared_high_block_plan_search(emu, t, k, min_rate):
+    """bg_shb_plan.h (host side of k_pairs_shb): the randomised coset search finds a plan for (nearly) every random L where
+    one can exist, every plan it returns satisfies the invariants the kernel relies on (nat a permutation, terms relabelled
+    by word-crossing bit swaps, one high pattern per class of 32, enough free low slots), and the search is deterministic
+    (the same L gives the same plan: the ranks of a multi-GPU job must agree)."""
+    rs = np.random.RandomState(1000 * t + k)
+    found = 0
+    n = 60
+    for _ in range(n):
+        L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(k)]
+        code, dg = emu.shb_plan_check(t, L)
+        assert code >= 0, (t, k, code, L)
+        assert (code, dg) == emu.shb_plan_check(t, L)
+        found += code
+    assert found >= min_rate * n, (t, k, found)
+    # degenerate L: repeated and zero rows (columns of rank < k)
+    L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(3)]
+    code, _ = emu.shb_plan_check(t, (L * k)[:k - 1] + [0])
+    assert code >= 0
