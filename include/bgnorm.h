@@ -204,6 +204,11 @@ int  bg_sampled_finish(bg_ctx* ctx, double norm, double* out);   /* wait for the
  * out[0] = G', out[1] = H'.  bg_sampled_norm2 = bg_sampled_prepare2 + run + bg_sampled_finish2. */
 int  bg_sampled_norm2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
                       uint64_t seed_g, uint64_t seed_h, double norm, double out[2]);
+/* Pipelining independent probability() evaluations (bins, circuits, the clients of a served back end): with a job in
+ * flight, bg_sampled_prepare2 may be called again with NEW projectors for a job of the same shape (samples, bins,
+ * seeds) — they are staged through alternating pinned buffers and uploaded behind the running job on its stream — and
+ * bg_set_decomposition with a new L of the same (t, k) keeps the prepared job and its captured CUDA graphs.  Then
+ * bg_sampled_run, and bg_sampled_finish2 for the OLDEST job.  A job of another shape drops what is in flight. */
 int  bg_sampled_prepare2(bg_ctx* ctx, const bg_projector* G, const bg_projector* H, uint64_t samples, int bins,
                          uint64_t seed_g, uint64_t seed_h);
 int  bg_sampled_finish2(bg_ctx* ctx, double norm, double out[2]);
