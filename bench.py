@@ -669,18 +669,26 @@ def main():
     # ---- end-to-end arm: the C-ABI calls a host makes per probability(): decomposition + both projectors from
     # HOST memory (the projectors are copied host -> pinned staging -> device every step; the decomposition is
     # recognised as unchanged and kept), the kernels, the all-reduce, the result back in host memory — every step.
-    Gs = [G, bg.Projector.from_buffer_copy(G)]                                  # two host copies that differ in an unused generator slot, so
-    Gs[1].xs[bg.MAX_STABS - 1] ^= 1                         # that every step's projectors really are new bytes to upload
+    # Every step's projectors really are new bytes to upload: a host copy whose unused last generator slot carries a
+    # step counter (the kernels read nstabs generators; the library compares the bytes with what the device holds, and
+    # in overlap mode there are two device copies used in turn — two alternating variants would never change either).
+    Gv = bg.Projector.from_buffer_copy(G)
+    e2e_serial = [0]
+
+    def fresh_G():
+        e2e_serial[0] += 1
+        Gv.xs[bg.MAX_STABS - 1] = e2e_serial[0]
+        return Gv
 
     def step_e2e(i):
         ctx.set_decomposition(t, exact, L)
-        return ctx.sampled_norm2(Gs[i & 1], H, samples, 1, 1001, 1002, 1.0)
+        return ctx.sampled_norm2(fresh_G(), H, samples, 1, 1001, 1002, 1.0)
 
     def submit_e2e(i):
         # the split-phase form of the same call (bg_sampled_prepare2 + bg_sampled_run): this step's projectors are
         # staged and uploaded, its kernels, all-reduce and read-back enqueued; bg_sampled_finish2 delivers the result
         ctx.set_decomposition(t, exact, L)
-        ctx.sampled_prepare2(Gs[i & 1], H, samples, 1, 1001, 1002)
+        ctx.sampled_prepare2(fresh_G(), H, samples, 1, 1001, 1002)
         ctx.sampled_run()
 
     for i in range(3):
@@ -712,6 +720,8 @@ def main():
     st = ctx.stats()
     e2e_value = pairs_per_step * args.steps / wall
     h2d = int(st["h2d_bytes"])
+    if h2d <= 0:
+        raise SystemExit("the end-to-end arm did not upload its step's projectors (h2d_bytes = 0): not an end-to-end number")
     d2h = int(st["d2h_bytes"])
 
     # ---- end-to-end with a NEW decomposition every step (what sampleQubits does: a fresh random L per probability()
