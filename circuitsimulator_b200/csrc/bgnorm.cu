@@ -1323,7 +1323,10 @@ template <typename W, int THREADS> static int launch_prepare_tps(bg_ctx* ctx, co
     const size_t smem = prep_tps_smem<W, THREADS>(a.t);
     int& per_sm = ctx->prep_ctas_per_sm[sizeof(W) == 8][THREADS == 32][a.t];
     if (per_sm == 0) {
-        CK(cudaFuncSetAttribute(k_prepare_tps<W, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the attribute is per kernel, not per launch: ask once for what the widest state of this word size needs (a
+        // smaller t seen later must not lower it under a larger t whose occupancy is already cached)
+        const size_t smem_max = prep_tps_smem<W, THREADS>(sizeof(W) == 8 ? BG_MAX_T : 32);
+        CK(cudaFuncSetAttribute(k_prepare_tps<W, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prepare_tps<W, THREADS>, THREADS, smem));
         if (per_sm < 1) return fail(ctx, "k_prepare_tps does not fit an SM at t = %d", a.t);
     }

@@ -513,6 +513,22 @@ def test_new_decomposition_of_the_same_shape_keeps_the_prepared_job(be):
     assert be.sampled_norm2(g, h, 600, 1, 21, 22, 1.0) == a
 
 
+def test_state_widths_in_any_order_on_one_context(be):
+    """One context, sampled jobs at t = 60, 40, 64, 33, 60 in this order: the draw + projection kernel's shared-memory
+    budget is a per-kernel attribute — a narrower state seen later must not shrink it under a wider one seen before
+    (each width's occupancy is cached).  Every job must run and repeat its own value."""
+    rs = np.random.RandomState(8)
+    seen = {}
+    for t in (60, 40, 64, 33, 60, 40):
+        P, _ = _random_projector(rs, t, 12) if t not in seen else (seen[t][0], None)
+        L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(6)] if t not in seen else seen[t][1]
+        be.set_decomposition(t, False, L)
+        val = be.sampled_norm2(P, P, 300, 1, 3, 4, 1.0)
+        if t in seen:
+            assert val == seen[t][2]
+        seen[t] = (P, L, val)
+
+
 def test_persistent_server_mode(tmp_path):
     """`bgbackend --serve <socket>` keeps the CUDA contexts alive across probability() calls; a client
     started with BG_SERVER=<socket> relays the same protocol."""
