@@ -61,6 +61,7 @@ class Emu:
                                          _P(C.c_uint64), _P(C.c_uint64)]
         lib.emu_shb_plan_check.argtypes = [C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_ulonglong)]
         lib.emu_shb_plan_check.restype = C.c_int
+        lib.emu_zw32_selftest.restype = C.c_int
         self.lib = lib
 
     def shb_plan_check(self, t, L):

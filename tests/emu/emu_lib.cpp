@@ -397,6 +397,24 @@ int emu_shb_plan_check(int t, int k, const uint64_t* Lrows, unsigned long long* 
     return 1;
 }
 
+// zw32_add (the 32-bit per-thread accumulation of k_pairs_shb) against zw_add for every (eps, p, m) a pair of
+// normalised states can give at 33 <= t <= 44, alone and summed over 128 worst-case terms.  Returns the mismatches.
+int emu_zw32_selftest(void) {
+    int bad = 0;
+    for (int t = 33; t <= ZW32_MAX_T; t++) {
+        const int sh = t / 2 + 1;
+        for (int eps = 0; eps <= 1; eps++)
+            for (int p = -t; p <= 0; p++)
+                for (int m = 0; m < 16; m++) {
+                    Zw a; Zw32 b;
+                    for (int j = 0; j < 4; j++) { a.a[j] = 0; b.a[j] = 0; }
+                    for (int rep = 0; rep < ZW32_MAX_TERMS; rep++) { zw_add(a, eps, p, m, sh); zw32_add(b, eps, p, m, sh); }
+                    for (int j = 0; j < 4; j++) if (a.a[j] != (long long)b.a[j]) bad++;
+                }
+    }
+    return bad;
+}
+
 int emu_expsum_selftest(int wordbits, unsigned long long seed, int trials) {
     return wordbits == 32 ? expsum_selftest<uint32_t>(seed, trials) : expsum_selftest<uint64_t>(seed, trials);
 }

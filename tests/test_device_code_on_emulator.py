@@ -311,3 +311,9 @@ def test_shared_high_block_plan_search(emu, t, k, min_rate):
     L = [int(rs.randint(0, 2 ** 62)) & ((1 << t) - 1) for _ in range(3)]
     code, _ = emu.shb_plan_check(t, (L * k)[:k - 1] + [0])
     assert code >= 0
+
+
+def test_32_bit_accumulation_equals_64_bit(emu):
+    """zw32_add — what a thread of k_pairs_shb adds its terms with — against zw_add over every (eps, p, m) of a pair of
+    normalised states at 33 <= t <= 44, 128 terms deep (the flush interval): same four integers, no overflow."""
+    assert emu.lib.emu_zw32_selftest() == 0
